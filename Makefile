@@ -1,0 +1,43 @@
+# Builds libfv2d_b200.so (CUDA kernels + C ABI, sm_100a only), the C++ host driver, and the
+# test oracles.  `python -c "import __graft_entry__ as g; g.build()"` runs `make all`.
+NVCC     ?= /usr/local/cuda/bin/nvcc
+ARCH     := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS  := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xcudafe --diag_suppress=177
+CSRC     := fv2d_b200/csrc
+OBJDIR   := build
+LIB      := fv2d_b200/libfv2d_b200.so
+HOSTHDR  := $(wildcard fv2d_b200/host/*.h) $(wildcard include/*.h) $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h)
+
+.PHONY: all lib driver oracle ref clean
+all: lib driver oracle
+
+lib: $(LIB)
+driver: fv2d_b200/fv2d_b200_main
+
+$(OBJDIR)/fv2d_ops.o: $(CSRC)/fv2d_ops.cu $(HOSTHDR)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) --fmad=false -c $< -o $@
+
+$(OBJDIR)/fv2d_sweep.o: $(CSRC)/fv2d_sweep.cu $(HOSTHDR)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(OBJDIR)/fv2d_sweep.ptxas.log || (cat $(OBJDIR)/fv2d_sweep.ptxas.log; false)
+
+$(OBJDIR)/fv2d_capi.o: $(CSRC)/fv2d_capi.cu $(HOSTHDR)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(OBJDIR)/fv2d_ops.o $(OBJDIR)/fv2d_sweep.o $(OBJDIR)/fv2d_capi.o
+	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static
+
+fv2d_b200/fv2d_b200_main: fv2d_b200/host/main.cpp $(HOSTHDR) $(LIB)
+	/usr/bin/g++ -std=c++17 -O2 -Wall -Iinclude fv2d_b200/host/main.cpp -o $@ -Lfv2d_b200 -lfv2d_b200 -Wl,-rpath,'$$ORIGIN'
+
+oracle:
+	$(MAKE) -C oracle oracle
+
+ref:
+	$(MAKE) -C oracle ref
+
+clean:
+	rm -rf $(OBJDIR) $(LIB) fv2d_b200/fv2d_b200_main
+	$(MAKE) -C oracle clean

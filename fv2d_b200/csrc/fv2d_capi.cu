@@ -1,0 +1,892 @@
+// fv2d_capi.cu — the C ABI (include/fv2d_b200.h): context management, host<->device
+// transfers, the operator-level entry points and the fused step driver.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <vector>
+
+#include "../host/Init.h"
+#include "../host/SimInfo.h"
+#include "fv2d_kernels.h"
+
+namespace fv2d
+{
+
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+  std::ostringstream os;
+  os << "CUDA error " << (int)e << " (" << cudaGetErrorString(e) << ") in " << what << " at " << file << ":" << line;
+  set_error(os.str());
+  return FV2D_ERR_CUDA;
+}
+static int arg_fail(const std::string &msg)
+{
+  set_error(msg);
+  return FV2D_ERR_ARG;
+}
+
+static IniOverrides parse_overrides(const char *ov)
+{
+  IniOverrides m;
+  if (!ov)
+    return m;
+  std::string s(ov);
+  size_t pos = 0;
+  while (pos < s.size())
+  {
+    size_t end = s.find(';', pos);
+    if (end == std::string::npos)
+      end = s.size();
+    std::string item = s.substr(pos, end - pos);
+    pos              = end + 1;
+    size_t eq = item.find('='), dot = item.find('.');
+    if (eq == std::string::npos || dot == std::string::npos || dot > eq)
+      continue;
+    auto trim = [](std::string x) {
+      size_t a = x.find_first_not_of(" \t"), b = x.find_last_not_of(" \t");
+      return a == std::string::npos ? std::string() : x.substr(a, b - a + 1);
+    };
+    m[IniFile::MakeKey(trim(item.substr(0, dot)), trim(item.substr(dot + 1, eq - dot - 1)))] = trim(item.substr(eq + 1));
+  }
+  return m;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda,
+// so the library still loads on a machine without a driver).
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_tmap(CUtensorMap *out, double *base, const Layout &L, int box_cols)
+{
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn)
+  {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    FV2D_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (!p || qres != cudaDriverEntryPointSuccess)
+    {
+      set_error("cuTensorMapEncodeTiled is not available in this driver");
+      return FV2D_ERR_CUDA;
+    }
+    fn = (PFN_encodeTiled)p;
+  }
+  // 3-D tensor: (column, row, field), fp64, row pitch and plane stride in bytes
+  cuuint64_t dims[3]    = {(cuuint64_t)L.pitch, (cuuint64_t)L.rows, 4};
+  cuuint64_t strides[2] = {(cuuint64_t)L.pitch * sizeof(double), (cuuint64_t)L.plane * sizeof(double)};
+  cuuint32_t box[3]     = {(cuuint32_t)box_cols, 1, 4};
+  cuuint32_t estr[3]    = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+  {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return FV2D_ERR_CUDA;
+  }
+  return FV2D_OK;
+}
+
+static size_t array_bytes(const Layout &L) { return (size_t)4 * L.plane * sizeof(double); }
+
+static int ensure_stage(fv2d_ctx *c, size_t bytes)
+{
+  if (c->stage_bytes >= bytes)
+    return FV2D_OK;
+  if (c->stage_host)
+    cudaFreeHost(c->stage_host);
+  c->stage_host  = nullptr;
+  c->stage_bytes = 0;
+  FV2D_CUDA(cudaMallocHost(&c->stage_host, bytes));
+  c->stage_bytes = bytes;
+  return FV2D_OK;
+}
+
+// host [f][rows][Ntx] <-> device padded planes
+static int copy_h2d(fv2d_ctx *c, double *dev, const double *host)
+{
+  const Layout &L = c->kp.L;
+  const int Ntx   = c->kp.p.Ntx;
+  for (int f = 0; f < 4; ++f)
+    FV2D_CUDA(cudaMemcpy2DAsync(dev + f * L.plane + L.lead, (size_t)L.pitch * sizeof(double),
+                                host + (size_t)f * L.rows * Ntx, (size_t)Ntx * sizeof(double),
+                                (size_t)Ntx * sizeof(double), (size_t)L.rows, cudaMemcpyHostToDevice, c->stream));
+  return FV2D_OK;
+}
+static int copy_d2h(fv2d_ctx *c, double *host, const double *dev)
+{
+  const Layout &L = c->kp.L;
+  const int Ntx   = c->kp.p.Ntx;
+  for (int f = 0; f < 4; ++f)
+    FV2D_CUDA(cudaMemcpy2DAsync(host + (size_t)f * L.rows * Ntx, (size_t)Ntx * sizeof(double),
+                                dev + f * L.plane + L.lead, (size_t)L.pitch * sizeof(double),
+                                (size_t)Ntx * sizeof(double), (size_t)L.rows, cudaMemcpyDeviceToHost, c->stream));
+  return FV2D_OK;
+}
+
+static int check_supported(const fv2d_device_params &p)
+{
+  if (p.Nx < 1 || p.Ny < 1)
+    return arg_fail("Nx and Ny must be positive");
+  if (p.Ng < 2)
+    return arg_fail("Nghosts >= 2 is required (stencil radius 2)");
+  if (p.Ntx != p.Nx + 2 * p.Ng || p.Nty != p.Ny + 2 * p.Ng || p.ibeg != p.Ng || p.jbeg != p.Ng ||
+      p.iend != p.Ng + p.Nx || p.jend != p.Ng + p.Ny)
+    return arg_fail("inconsistent mesh extents in fv2d_device_params");
+  if (p.thermal_conductivity_active && p.thermal_conductivity_mode != FV2D_TCM_CONSTANT)
+    return arg_fail("thermal conductivity mode B02 is undefined behaviour in the reference (its parameters are never "
+                    "read) and is not supported");
+  if ((p.boundary_x == FV2D_BC_PERIODIC && p.Nx < p.Ng) || (p.boundary_y == FV2D_BC_PERIODIC && p.Ny < p.Ng))
+    return arg_fail("periodic direction narrower than the ghost layer");
+  return FV2D_OK;
+}
+
+static int sync_ctx(fv2d_ctx *c)
+{
+  FV2D_CUDA(cudaStreamSynchronize(c->stream));
+  return FV2D_OK;
+}
+
+static int read_scalars(fv2d_ctx *c)
+{
+  FV2D_CUDA(cudaMemcpyAsync(c->sc_host, c->sc, offsetof(DevScalars, dt_hist), cudaMemcpyDeviceToHost, c->stream));
+  return sync_ctx(c);
+}
+
+// ------------------------------------------------------------------ step drivers
+
+static int ensure_slopes(fv2d_ctx *c)
+{
+  if (c->slopesX)
+    return FV2D_OK;
+  const size_t bytes = array_bytes(c->kp.L);
+  FV2D_CUDA(cudaMalloc(&c->slopesX, bytes));
+  FV2D_CUDA(cudaMalloc(&c->slopesY, bytes));
+  FV2D_CUDA(cudaMemsetAsync(c->slopesX, 0, bytes, c->stream)); // zero-filled like Update.h:54-55
+  FV2D_CUDA(cudaMemsetAsync(c->slopesY, 0, bytes, c->stream));
+  return FV2D_OK;
+}
+static int ensure_ustar(fv2d_ctx *c)
+{
+  if (c->Ustar)
+    return FV2D_OK;
+  const size_t bytes = array_bytes(c->kp.L);
+  FV2D_CUDA(cudaMalloc(&c->Ustar, bytes));
+  FV2D_CUDA(cudaMemsetAsync(c->Ustar, 0, bytes, c->stream));
+  return FV2D_OK;
+}
+
+// Update.h:176-191 with the operator-level kernels
+static int euler_step_ops(fv2d_ctx *c, double *Q, double *Unew, double dt)
+{
+  int rc;
+  launch_fill_boundaries(c->kp, Q, c->stream);
+  if (c->kp.p.reconstruction == FV2D_PLM)
+  {
+    if ((rc = ensure_slopes(c)))
+      return rc;
+    launch_compute_slopes(c->kp, Q, c->slopesX, c->slopesY, c->stream);
+  }
+  // (PCM never reads the slope arrays: Update.h:27-33)
+  launch_fluxes_and_update(c->kp, Q, c->slopesX, c->slopesY, Unew, dt, c->stream);
+  if (c->kp.p.thermal_conductivity_active)
+    launch_thermal_conduction(c->kp, Q, Unew, dt, c->stream);
+  if (c->kp.p.viscosity_active)
+    launch_viscosity(c->kp, Q, Unew, dt, c->stream);
+  FV2D_CUDA(cudaGetLastError());
+  return FV2D_OK;
+}
+
+static int choose_chunk_rows(const fv2d_ctx *c)
+{
+  const char *env = std::getenv("FV2D_CHUNK_ROWS");
+  if (env && std::atoi(env) > 0)
+    return std::atoi(env);
+  return c->kp.p.Ny < 64 ? c->kp.p.Ny : 64;
+}
+
+// One fused time step (Euler: 1 sweep; RK2: 2 sweeps), dt either from the host or from the
+// device-resident CFL maximum of the current state.
+static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
+{
+  if (!c->tmap_ok)
+    return arg_fail("TMA descriptors unavailable");
+  const int cur = c->cur, nxt = cur ^ 1;
+  StepBeginArgs b;
+  b.use_device_dt = device_dt ? 1 : 0;
+  b.dt_host       = dt_host;
+  b.acc_read      = c->acc_parity;
+  b.acc_reset     = c->acc_parity ^ 1;
+  b.advance       = 1;
+  launch_step_begin(c->kp, c->Q[cur], b, c->stream);
+
+  SweepArgs a;
+  a.kp         = c->kp;
+  a.chunk_rows = choose_chunk_rows(c);
+  a.n_strips   = 0;
+  a.acc_slot   = c->acc_parity ^ 1;
+  cudaError_t e;
+  if (c->time_stepping == FV2D_TS_RK2)
+  {
+    int rc;
+    if ((rc = ensure_ustar(c)))
+      return rc;
+    // stage 1: U* = U + dt L(Q), Q* = consToPrim(U*)           (Update.h:204-210)
+    a.Uin = c->U, a.Uout = c->Ustar, a.U0 = nullptr, a.Qout = c->Q[nxt], a.final_stage = 0;
+    e = launch_sweep(c->tmapQ[cur], a, c->stream);
+    if (e != cudaSuccess)
+      return cuda_fail(e, "sweep stage 1", __FILE__, __LINE__);
+    // ghosts of Q*, no clock advance                              (Update.h:211 -> :179)
+    b.advance = 0;
+    launch_step_begin(c->kp, c->Q[nxt], b, c->stream);
+    // stage 2: U = 0.5 (U0 + U* + dt L(Q*)), Q = consToPrim(U)    (Update.h:211-220, main.cpp:80-81)
+    a.Uin = c->Ustar, a.Uout = c->U, a.U0 = c->U, a.Qout = c->Q[cur], a.final_stage = 1;
+    e = launch_sweep(c->tmapQ[nxt], a, c->stream);
+    if (e != cudaSuccess)
+      return cuda_fail(e, "sweep stage 2", __FILE__, __LINE__);
+    // Q[cur] holds the new state again
+  }
+  else
+  {
+    a.Uin = c->U, a.Uout = c->U, a.U0 = nullptr, a.Qout = c->Q[nxt], a.final_stage = 1;
+    e = launch_sweep(c->tmapQ[cur], a, c->stream);
+    if (e != cudaSuccess)
+      return cuda_fail(e, "sweep", __FILE__, __LINE__);
+    c->cur = nxt;
+  }
+  c->acc_parity ^= 1;
+  return FV2D_OK;
+}
+
+// standalone computeDt of the current state into inv_acc[acc_parity] and sc->dt
+static int compute_dt_now(fv2d_ctx *c)
+{
+  unsigned long long init = FV2D_ENC_NEG_MAX;
+  FV2D_CUDA(cudaMemcpyAsync(&c->sc->inv_acc[c->acc_parity][0], &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+  launch_compute_dt(c->kp, c->Q[c->cur], &c->sc->inv_acc[c->acc_parity][0], c->stream);
+  launch_finalize_dt(c->kp, &c->sc->inv_acc[c->acc_parity][0], c->stream);
+  FV2D_CUDA(cudaGetLastError());
+  return FV2D_OK;
+}
+
+} // namespace fv2d
+
+using namespace fv2d;
+
+// ====================================================================================== C ABI
+
+extern "C" {
+
+const char *fv2d_last_error(void) { return g_last_error.c_str(); }
+int fv2d_abi_version(void) { return 1; }
+
+int fv2d_params_from_ini(const char *ini_path, const char *overrides, fv2d_device_params *dev, fv2d_run_params *run)
+{
+  if (!ini_path || !dev || !run)
+    return arg_fail("null argument");
+  try
+  {
+    {
+      std::ifstream probe(ini_path);
+      if (!probe.good())
+      {
+        set_error(std::string("cannot open ini file ") + ini_path);
+        return FV2D_ERR_IO;
+      }
+    }
+    Params prm = readInifile(ini_path, parse_overrides(overrides));
+    *dev       = prm.device_params;
+    *run       = prm.run_pod();
+  }
+  catch (const std::exception &e)
+  {
+    set_error(e.what());
+    return FV2D_ERR_CONFIG;
+  }
+  return FV2D_OK;
+}
+
+int fv2d_params_dump_ini(const char *ini_path, const char *overrides, const char *out_path)
+{
+  if (!ini_path || !out_path)
+    return arg_fail("null argument");
+  try
+  {
+    std::ostringstream sink;
+    Params prm = readInifile(ini_path, parse_overrides(overrides), sink);
+    std::ofstream out(out_path);
+    if (!out.good())
+    {
+      set_error(std::string("cannot write ") + out_path);
+      return FV2D_ERR_IO;
+    }
+    prm.reader.outputValues(out);
+  }
+  catch (const std::exception &e)
+  {
+    set_error(e.what());
+    return FV2D_ERR_CONFIG;
+  }
+  return FV2D_OK;
+}
+
+int fv2d_init_problem(const fv2d_device_params *dev, const fv2d_run_params *run, double *hostQ)
+{
+  if (!dev || !run || !hostQ)
+    return arg_fail("null argument");
+  try
+  {
+    Params prm;
+    static_cast<fv2d_device_params &>(prm.device_params) = *dev;
+    prm.problem                                           = run->problem;
+    prm.seed                                              = run->seed;
+    InitFunctor init(prm);
+    HostArray Q(dev->Nty, dev->Ntx);
+    init.init(Q);
+    std::memcpy(hostQ, Q.data.data(), Q.data.size() * sizeof(double));
+  }
+  catch (const std::exception &e)
+  {
+    set_error(e.what());
+    return FV2D_ERR_CONFIG;
+  }
+  return FV2D_OK;
+}
+
+int fv2d_ctx_create_slab(const fv2d_device_params *dev, int time_stepping, double eps_reset_negative, int device,
+                         int rank, int nranks, fv2d_ctx **out)
+{
+  if (!dev || !out)
+    return arg_fail("null argument");
+  *out = nullptr;
+  int rc;
+  if ((rc = check_supported(*dev)))
+    return rc;
+  if (nranks < 1 || rank < 0 || rank >= nranks || dev->Ny % nranks != 0)
+    return arg_fail("bad slab decomposition: Ny must be divisible by nranks");
+  if (time_stepping != FV2D_TS_EULER && time_stepping != FV2D_TS_RK2)
+    return arg_fail("time_stepping must be FV2D_TS_EULER or FV2D_TS_RK2");
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+  {
+    set_error("no CUDA device available (this library has no CPU fallback)");
+    return FV2D_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev)
+    return arg_fail("device index out of range");
+  FV2D_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  FV2D_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+  {
+    set_error(std::string("device '") + prop.name + "' is not sm_100: the kernels are built for sm_100a only");
+    return FV2D_ERR_CUDA;
+  }
+
+  fv2d_ctx *c = new fv2d_ctx();
+  std::memset(c, 0, sizeof *c);
+  c->glob          = *dev;
+  c->time_stepping = time_stepping;
+  c->device        = device;
+  c->rank          = rank;
+  c->nranks        = nranks;
+
+  KParams &kp  = c->kp;
+  kp.p         = *dev;
+  const int Nyl = dev->Ny / nranks;
+  kp.p.Ny       = Nyl;
+  kp.p.Nty      = Nyl + 2 * dev->Ng;
+  kp.p.jend     = dev->Ng + Nyl;
+  kp.Ny_global  = dev->Ny;
+  kp.j_global_offset = rank * Nyl;
+  const bool periodic_y = dev->boundary_y == FV2D_BC_PERIODIC;
+  kp.edge_lo = (rank == 0 && !(periodic_y && nranks > 1)) ? EDGE_PHYSICAL : EDGE_NEIGHBOUR;
+  kp.edge_hi = (rank == nranks - 1 && !(periodic_y && nranks > 1)) ? EDGE_PHYSICAL : EDGE_NEIGHBOUR;
+  kp.eps_reset = eps_reset_negative;
+
+  Layout &L = kp.L;
+  L.lead    = (16 - dev->ibeg % 16) % 16;
+  L.pitch   = ((L.lead + dev->Ntx + 15) / 16) * 16;
+  // room for the TMA box of the last strip to stay inside the row where possible
+  L.rows  = kp.p.Nty;
+  L.plane = (long long)L.pitch * L.rows;
+
+  auto fail = [&](int code) {
+    fv2d_ctx_destroy(c);
+    return code;
+  };
+#define FV2D_TRY(call)                                              \
+  do                                                                \
+  {                                                                 \
+    cudaError_t e__ = (call);                                       \
+    if (e__ != cudaSuccess)                                         \
+      return fail(cuda_fail(e__, #call, __FILE__, __LINE__));       \
+  } while (0)
+
+  FV2D_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->own_stream = true;
+  const size_t bytes = array_bytes(L);
+  FV2D_TRY(cudaMalloc(&c->Q[0], bytes));
+  FV2D_TRY(cudaMalloc(&c->Q[1], bytes));
+  FV2D_TRY(cudaMalloc(&c->U, bytes));
+  FV2D_TRY(cudaMemsetAsync(c->Q[0], 0, bytes, c->stream));
+  FV2D_TRY(cudaMemsetAsync(c->Q[1], 0, bytes, c->stream));
+  FV2D_TRY(cudaMemsetAsync(c->U, 0, bytes, c->stream));
+  FV2D_TRY(cudaMalloc(&c->sc, sizeof(DevScalars)));
+  FV2D_TRY(cudaMemsetAsync(c->sc, 0, sizeof(DevScalars), c->stream));
+  FV2D_TRY(cudaMallocHost(&c->sc_host, sizeof(DevScalars)));
+  std::memset(c->sc_host, 0, sizeof(DevScalars));
+  kp.sc = c->sc;
+
+  // analytical gravity profile: glibc sin() on the host, narrowed to float (Gravity.h:15-29, Q5)
+  if (dev->gravity_mode == FV2D_GRAV_ANALYTICAL)
+  {
+    std::vector<double> g(kp.p.Nty);
+    for (int j = 0; j < kp.p.Nty; ++j)
+    {
+      const int jg   = j + kp.j_global_offset;
+      const double y = dev->ymin + (jg - dev->jbeg + 0.5) * dev->dy;
+      g[j]           = (double)(float)(dev->hot_bubble_g0 * std::sin(y * M_PI * 2.0 / dev->ymax));
+    }
+    FV2D_TRY(cudaMalloc(&c->gtab, g.size() * sizeof(double)));
+    FV2D_TRY(cudaMemcpyAsync(c->gtab, g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    FV2D_TRY(cudaStreamSynchronize(c->stream));
+  }
+  kp.gtab = c->gtab;
+
+  // inverse-dt accumulators start at the Max identity
+  {
+    DevScalars init;
+    std::memset(&init, 0, sizeof init);
+    for (int a = 0; a < 2; ++a)
+      for (int k = 0; k < 4; ++k)
+        init.inv_acc[a][k] = FV2D_ENC_NEG_MAX;
+    FV2D_TRY(cudaMemcpyAsync(c->sc, &init, offsetof(DevScalars, dt_hist), cudaMemcpyHostToDevice, c->stream));
+    FV2D_TRY(cudaStreamSynchronize(c->stream));
+  }
+
+  FV2D_TRY(sweep_configure());
+  c->tmap_ok = (make_tmap(&c->tmapQ[0], c->Q[0], L, sweep_strip_width() + 4) == FV2D_OK) &&
+               (make_tmap(&c->tmapQ[1], c->Q[1], L, sweep_strip_width() + 4) == FV2D_OK);
+  if (!c->tmap_ok)
+    return fail(FV2D_ERR_CUDA);
+#undef FV2D_TRY
+  *out = c;
+  return FV2D_OK;
+}
+
+int fv2d_ctx_create(const fv2d_device_params *dev, int time_stepping, double eps_reset_negative, int device,
+                    fv2d_ctx **out)
+{
+  return fv2d_ctx_create_slab(dev, time_stepping, eps_reset_negative, device, 0, 1, out);
+}
+
+void fv2d_ctx_destroy(fv2d_ctx *c)
+{
+  if (!c)
+    return;
+  cudaSetDevice(c->device);
+  if (c->stream)
+    cudaStreamSynchronize(c->stream);
+  for (int k = 0; k < c->n_ipc_opened; ++k)
+    cudaIpcCloseMemHandle(c->ipc_opened[k]);
+  cudaFree(c->Q[0]);
+  cudaFree(c->Q[1]);
+  cudaFree(c->U);
+  cudaFree(c->Ustar);
+  cudaFree(c->slopesX);
+  cudaFree(c->slopesY);
+  cudaFree(c->gtab);
+  cudaFree(c->sc);
+  if (c->sc_host)
+    cudaFreeHost(c->sc_host);
+  if (c->stage_host)
+    cudaFreeHost(c->stage_host);
+  if (c->own_stream && c->stream)
+    cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int fv2d_ctx_set_stream(fv2d_ctx *c, void *cuda_stream)
+{
+  if (!c)
+    return arg_fail("null context");
+  FV2D_CUDA(cudaSetDevice(c->device));
+  FV2D_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->own_stream)
+    cudaStreamDestroy(c->stream);
+  c->stream     = (cudaStream_t)cuda_stream;
+  c->own_stream = false;
+  return FV2D_OK;
+}
+
+int fv2d_sync(fv2d_ctx *c)
+{
+  if (!c)
+    return arg_fail("null context");
+  FV2D_CUDA(cudaSetDevice(c->device));
+  return sync_ctx(c);
+}
+
+int fv2d_ctx_geometry(const fv2d_ctx *c, int64_t out[6])
+{
+  if (!c || !out)
+    return arg_fail("null argument");
+  out[0] = c->kp.p.Ntx;
+  out[1] = c->kp.p.Nty;
+  out[2] = c->kp.p.Ny;
+  out[3] = c->kp.j_global_offset;
+  out[4] = c->kp.L.pitch;
+  out[5] = c->kp.L.lead;
+  return FV2D_OK;
+}
+
+#define FV2D_ENTER(c)                       \
+  if (!(c))                                 \
+    return arg_fail("null context");        \
+  FV2D_CUDA(cudaSetDevice((c)->device));
+
+int fv2d_upload_Q(fv2d_ctx *c, const double *hostQ)
+{
+  FV2D_ENTER(c);
+  if (!hostQ)
+    return arg_fail("null host array");
+  int rc = copy_h2d(c, c->Q[c->cur], hostQ);
+  return rc ? rc : sync_ctx(c);
+}
+int fv2d_upload_U(fv2d_ctx *c, const double *hostU)
+{
+  FV2D_ENTER(c);
+  if (!hostU)
+    return arg_fail("null host array");
+  int rc = copy_h2d(c, c->U, hostU);
+  return rc ? rc : sync_ctx(c);
+}
+int fv2d_download_Q(fv2d_ctx *c, double *hostQ)
+{
+  FV2D_ENTER(c);
+  if (!hostQ)
+    return arg_fail("null host array");
+  int rc = copy_d2h(c, hostQ, c->Q[c->cur]);
+  return rc ? rc : sync_ctx(c);
+}
+int fv2d_download_U(fv2d_ctx *c, double *hostU)
+{
+  FV2D_ENTER(c);
+  if (!hostU)
+    return arg_fail("null host array");
+  int rc = copy_d2h(c, hostU, c->U);
+  return rc ? rc : sync_ctx(c);
+}
+
+int fv2d_prim_to_cons(fv2d_ctx *c)
+{
+  FV2D_ENTER(c);
+  launch_prim_to_cons(c->kp, c->Q[c->cur], c->U, c->stream);
+  FV2D_CUDA(cudaGetLastError());
+  return FV2D_OK;
+}
+int fv2d_cons_to_prim(fv2d_ctx *c)
+{
+  FV2D_ENTER(c);
+  launch_cons_to_prim(c->kp, c->U, c->Q[c->cur], c->stream);
+  FV2D_CUDA(cudaGetLastError());
+  return FV2D_OK;
+}
+int fv2d_check_negatives(fv2d_ctx *c, uint64_t counts[3])
+{
+  FV2D_ENTER(c);
+  int rc;
+  if ((rc = read_scalars(c)))
+    return rc;
+  unsigned long long before[3] = {c->sc_host->neg[0], c->sc_host->neg[1], c->sc_host->neg[2]};
+  launch_check_negatives(c->kp, c->Q[c->cur], c->sc->neg, c->stream);
+  FV2D_CUDA(cudaGetLastError());
+  if ((rc = read_scalars(c)))
+    return rc;
+  if (counts)
+    for (int k = 0; k < 3; ++k)
+      counts[k] = c->sc_host->neg[k] - before[k];
+  return FV2D_OK;
+}
+int fv2d_fill_boundaries(fv2d_ctx *c)
+{
+  FV2D_ENTER(c);
+  launch_fill_boundaries(c->kp, c->Q[c->cur], c->stream);
+  FV2D_CUDA(cudaGetLastError());
+  return FV2D_OK;
+}
+int fv2d_compute_dt(fv2d_ctx *c, double *dt, double inv_dt[3])
+{
+  FV2D_ENTER(c);
+  int rc;
+  if ((rc = compute_dt_now(c)))
+    return rc;
+  if ((rc = read_scalars(c)))
+    return rc;
+  if (dt)
+    *dt = c->sc_host->dt;
+  if (inv_dt)
+    for (int k = 0; k < 3; ++k)
+      inv_dt[k] = c->sc_host->inv_dt_last[k];
+  return FV2D_OK;
+}
+int fv2d_compute_slopes(fv2d_ctx *c)
+{
+  FV2D_ENTER(c);
+  int rc;
+  if ((rc = ensure_slopes(c)))
+    return rc;
+  launch_compute_slopes(c->kp, c->Q[c->cur], c->slopesX, c->slopesY, c->stream);
+  FV2D_CUDA(cudaGetLastError());
+  return FV2D_OK;
+}
+int fv2d_compute_fluxes_and_update(fv2d_ctx *c, double dt)
+{
+  FV2D_ENTER(c);
+  int rc;
+  if ((rc = ensure_slopes(c)))
+    return rc;
+  launch_fluxes_and_update(c->kp, c->Q[c->cur], c->slopesX, c->slopesY, c->U, dt, c->stream);
+  FV2D_CUDA(cudaGetLastError());
+  return FV2D_OK;
+}
+int fv2d_apply_thermal_conduction(fv2d_ctx *c, double dt)
+{
+  FV2D_ENTER(c);
+  launch_thermal_conduction(c->kp, c->Q[c->cur], c->U, dt, c->stream);
+  FV2D_CUDA(cudaGetLastError());
+  return FV2D_OK;
+}
+int fv2d_apply_viscosity(fv2d_ctx *c, double dt)
+{
+  FV2D_ENTER(c);
+  launch_viscosity(c->kp, c->Q[c->cur], c->U, dt, c->stream);
+  FV2D_CUDA(cudaGetLastError());
+  return FV2D_OK;
+}
+int fv2d_euler_step(fv2d_ctx *c, double dt)
+{
+  FV2D_ENTER(c);
+  return euler_step_ops(c, c->Q[c->cur], c->U, dt);
+}
+int fv2d_update(fv2d_ctx *c, double dt)
+{
+  FV2D_ENTER(c);
+  if (c->time_stepping == FV2D_TS_EULER)
+    return euler_step_ops(c, c->Q[c->cur], c->U, dt);
+  // SSP-RK2, Update.h:197-221
+  int rc;
+  if ((rc = ensure_ustar(c)))
+    return rc;
+  const size_t bytes = array_bytes(c->kp.L);
+  double *Q = c->Q[c->cur], *U0 = c->Q[c->cur ^ 1]; // the spare Q buffer doubles as U0
+  FV2D_CUDA(cudaMemcpyAsync(U0, c->U, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  FV2D_CUDA(cudaMemcpyAsync(c->Ustar, c->U, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  if ((rc = euler_step_ops(c, Q, c->Ustar, dt)))
+    return rc;
+  FV2D_CUDA(cudaMemcpyAsync(c->U, c->Ustar, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  launch_cons_to_prim(c->kp, c->Ustar, Q, c->stream);
+  if ((rc = euler_step_ops(c, Q, c->U, dt)))
+    return rc;
+  launch_rk2_correct(c->kp, U0, c->U, c->stream);
+  FV2D_CUDA(cudaGetLastError());
+  return FV2D_OK;
+}
+
+int fv2d_step(fv2d_ctx *c, double dt)
+{
+  FV2D_ENTER(c);
+  return fused_step(c, false, dt);
+}
+int fv2d_step_device_dt(fv2d_ctx *c)
+{
+  FV2D_ENTER(c);
+  return fused_step(c, true, 0.0);
+}
+int fv2d_run_steps(fv2d_ctx *c, int64_t nsteps)
+{
+  FV2D_ENTER(c);
+  for (int64_t k = 0; k < nsteps; ++k)
+  {
+    int rc = fused_step(c, true, 0.0);
+    if (rc)
+      return rc;
+  }
+  return FV2D_OK;
+}
+int fv2d_run_until(fv2d_ctx *c, double tend, int64_t max_steps, int64_t *steps_done)
+{
+  FV2D_ENTER(c);
+  int rc;
+  int64_t n = 0;
+  if ((rc = read_scalars(c)))
+    return rc;
+  double t = c->sc_host->t;
+  // main.cpp:62: while (t + epsilon < tend)
+  while (t + c->glob.epsilon < tend && n < max_steps)
+  {
+    if ((rc = fused_step(c, true, 0.0)))
+      return rc;
+    if ((rc = read_scalars(c)))
+      return rc;
+    t = c->sc_host->t;
+    ++n;
+  }
+  if (steps_done)
+    *steps_done = n;
+  return FV2D_OK;
+}
+
+int fv2d_get_time(fv2d_ctx *c, double *t, double *next_dt, int64_t *steps)
+{
+  FV2D_ENTER(c);
+  int rc;
+  if ((rc = read_scalars(c)))
+    return rc;
+  if (t)
+    *t = c->sc_host->t;
+  if (steps)
+    *steps = c->sc_host->step;
+  if (next_dt)
+  {
+    // what step_begin would compute from the current accumulator
+    const fv2d_device_params &p = c->kp.p;
+    double hyp = decode_ordered(c->sc_host->inv_acc[c->acc_parity][0]);
+    double tc = p.epsilon, visc = p.epsilon;
+    if (p.thermal_conductivity_active)
+      tc = std::fmax(2.0 * p.kappa / (p.dx * p.dx), 2.0 * p.kappa / (p.dy * p.dy));
+    if (p.viscosity_active)
+      visc = std::fmax(2.0 * p.mu / (p.dx * p.dx), 2.0 * p.mu / (p.dy * p.dy));
+    double m = hyp;
+    if (m < tc)
+      m = tc;
+    if (m < visc)
+      m = visc;
+    *next_dt = p.CFL / m;
+  }
+  return FV2D_OK;
+}
+int fv2d_set_time(fv2d_ctx *c, double t)
+{
+  FV2D_ENTER(c);
+  FV2D_CUDA(cudaMemcpyAsync(&c->sc->t, &t, sizeof t, cudaMemcpyHostToDevice, c->stream));
+  return sync_ctx(c);
+}
+int fv2d_get_dt_history(fv2d_ctx *c, double *dts, int64_t n, int64_t *n_out)
+{
+  FV2D_ENTER(c);
+  if (!dts)
+    return arg_fail("null output");
+  FV2D_CUDA(cudaMemcpyAsync(c->sc_host, c->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
+  int rc;
+  if ((rc = sync_ctx(c)))
+    return rc;
+  const int64_t steps = c->sc_host->step;
+  int64_t m           = n;
+  if (m > steps)
+    m = steps;
+  if (m > FV2D_DT_HISTORY)
+    m = FV2D_DT_HISTORY;
+  for (int64_t k = 0; k < m; ++k)
+    dts[k] = c->sc_host->dt_hist[(steps - m + k) % FV2D_DT_HISTORY];
+  if (n_out)
+    *n_out = m;
+  return FV2D_OK;
+}
+int fv2d_get_negative_counts(fv2d_ctx *c, uint64_t counts[3], int reset)
+{
+  FV2D_ENTER(c);
+  int rc;
+  if ((rc = read_scalars(c)))
+    return rc;
+  if (counts)
+    for (int k = 0; k < 3; ++k)
+      counts[k] = c->sc_host->neg[k];
+  if (reset)
+  {
+    FV2D_CUDA(cudaMemsetAsync(c->sc->neg, 0, sizeof(c->sc->neg), c->stream));
+    return sync_ctx(c);
+  }
+  return FV2D_OK;
+}
+int fv2d_get_inv_dt(fv2d_ctx *c, double inv_dt[3])
+{
+  FV2D_ENTER(c);
+  int rc;
+  if ((rc = read_scalars(c)))
+    return rc;
+  for (int k = 0; k < 3; ++k)
+    inv_dt[k] = c->sc_host->inv_dt_last[k];
+  return FV2D_OK;
+}
+int fv2d_integrate_mass_energy(fv2d_ctx *c, double *mass, double *energy)
+{
+  FV2D_ENTER(c);
+  double *rowsum = nullptr;
+  FV2D_CUDA(cudaMalloc(&rowsum, (size_t)2 * c->kp.p.Ny * sizeof(double)));
+  launch_mass_energy(c->kp, c->U, rowsum, c->stream);
+  int rc = read_scalars(c);
+  cudaFree(rowsum);
+  if (rc)
+    return rc;
+  if (mass)
+    *mass = c->sc_host->sums[0];
+  if (energy)
+    *energy = c->sc_host->sums[1];
+  return FV2D_OK;
+}
+
+int fv2d_advance_host(fv2d_ctx *c, const double *hostQ_in, double *hostQ_out, int64_t nsteps, double *dts)
+{
+  FV2D_ENTER(c);
+  if (!hostQ_in || !hostQ_out)
+    return arg_fail("null host array");
+  int rc;
+  if ((rc = copy_h2d(c, c->Q[c->cur], hostQ_in)))
+    return rc;
+  launch_prim_to_cons(c->kp, c->Q[c->cur], c->U, c->stream);
+  if ((rc = compute_dt_now(c)))
+    return rc;
+  for (int64_t k = 0; k < nsteps; ++k)
+    if ((rc = fused_step(c, true, 0.0)))
+      return rc;
+  if ((rc = copy_d2h(c, hostQ_out, c->Q[c->cur])))
+    return rc;
+  if (dts)
+  {
+    int64_t got = 0;
+    return fv2d_get_dt_history(c, dts, nsteps, &got);
+  }
+  return sync_ctx(c);
+}
+
+// ------------------------------------------------------------------ multi-GPU halo exchange
+
+int fv2d_halo_export(fv2d_ctx *c, void *handle)
+{
+  FV2D_ENTER(c);
+  (void)handle;
+  return arg_fail("halo exchange: not implemented yet");
+}
+int fv2d_halo_connect(fv2d_ctx *c, const void *handles, int nranks)
+{
+  FV2D_ENTER(c);
+  (void)handles;
+  (void)nranks;
+  return arg_fail("halo exchange: not implemented yet");
+}
+int fv2d_halo_connect_local(fv2d_ctx **ctxs, int nranks)
+{
+  (void)ctxs;
+  (void)nranks;
+  return arg_fail("halo exchange: not implemented yet");
+}
+
+} // extern "C"

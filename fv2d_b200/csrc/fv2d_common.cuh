@@ -1,0 +1,140 @@
+// fv2d_common.cuh — shared declarations of the CUDA side: device array layout, kernel
+// parameter block, context, error helpers.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/fv2d_b200.h"
+
+namespace fv2d
+{
+
+// ---------------------------------------------------------------------------------------
+// Device array layout.  One "array" (the reference's View<double***>(Nty,
+// Ntx, 4), main.cpp:33-34) is 4 SoA planes.  A plane is Nty rows of `pitch` doubles; cell
+// (i, j) sits at column lead + i, where lead is chosen so that the first DOMAIN cell
+// (i = ibeg) starts a 128-byte line, and pitch is a multiple of 16 doubles so every row
+// starts one too.  => warp-wide stores of domain cells are whole 128-byte lines, and the
+// row pitch satisfies the 16-byte stride rule of TMA tensor maps.
+// ---------------------------------------------------------------------------------------
+struct Layout
+{
+  int pitch;       // doubles per row
+  int lead;        // column of cell i = 0
+  int rows;        // Nty of the local slab
+  long long plane; // doubles per field plane (= pitch * rows)
+  __host__ __device__ inline long long at(int f, int i, int j) const
+  {
+    return (long long)f * plane + (long long)j * pitch + lead + i;
+  }
+};
+
+// What lies beyond the low-j / high-j edge of the local slab.
+enum : int
+{
+  EDGE_PHYSICAL = 0, // the global boundary: apply boundary_y
+  EDGE_NEIGHBOUR = 1 // another rank's slab: ghost rows come from the halo exchange
+};
+
+// Device-resident scalars of one context (one 128-byte-aligned block).
+struct DevScalars
+{
+  double dt;                        // dt of the step being / about to be taken
+  double t;                         // simulated time
+  long long step;                   // steps taken
+  unsigned long long inv_acc[2][4]; // order-preserving-encoded maxima {hyp, tc, visc, -} ; [parity]
+  unsigned long long neg[4];        // cumulative {rho<0, P<0, NaN, -}
+  double inv_dt_last[4];            // decoded maxima behind `dt`
+  double sums[2];                   // scratch for mass/energy integration
+  double dt_hist[FV2D_DT_HISTORY];  // ring of dts used
+};
+
+// Parameter block handed to every kernel by value.
+struct KParams
+{
+  fv2d_device_params p; // LOCAL slab view: Ny/Nty/jbeg/jend describe the slab
+  Layout L;
+  int edge_lo, edge_hi;  // EDGE_* of the slab's low-j / high-j side
+  int j_global_offset;   // global row index of local row 0
+  int Ny_global;
+  double eps_reset;
+  const double *gtab;    // per-local-row analytical gravity (float-valued), or nullptr
+  DevScalars *sc;
+};
+
+// Monotone map double -> uint64 so that atomicMax on the integer orders like the double.
+__host__ __device__ inline unsigned long long encode_ordered(double x)
+{
+#ifdef __CUDA_ARCH__
+  unsigned long long b = (unsigned long long)__double_as_longlong(x);
+#else
+  unsigned long long b;
+  memcpy(&b, &x, sizeof b);
+#endif
+  return (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
+}
+__host__ __device__ inline double decode_ordered(unsigned long long e)
+{
+  unsigned long long b = (e & 0x8000000000000000ULL) ? (e & 0x7fffffffffffffffULL) : ~e;
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double((long long)b);
+#else
+  double x;
+  memcpy(&x, &b, sizeof x);
+  return x;
+#endif
+}
+// encode_ordered(-DBL_MAX): identity of the Max reducers (Kokkos::Max, ComputeDt.h:50-52)
+#define FV2D_ENC_NEG_MAX 0x0010000000000000ULL
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define FV2D_CUDA(call)                                                  \
+  do                                                                     \
+  {                                                                      \
+    cudaError_t e__ = (call);                                            \
+    if (e__ != cudaSuccess)                                              \
+      return ::fv2d::cuda_fail(e__, #call, __FILE__, __LINE__);          \
+  } while (0)
+
+} // namespace fv2d
+
+// The context behind the opaque C handle.
+struct fv2d_ctx
+{
+  fv2d::KParams kp;        // local parameters + layout
+  fv2d_device_params glob; // global grid
+  int time_stepping;
+  int device;
+  int rank, nranks;
+  cudaStream_t stream;
+  bool own_stream;
+
+  double *Q[2]; // ping-pong primitive arrays; Q[cur] is "the" Q
+  int cur;
+  double *U;      // conservative
+  double *Ustar;  // RK2 stage buffer (lazy)
+  double *slopesX, *slopesY; // operator-level API only (lazy)
+  double *gtab;   // analytical gravity table (or nullptr)
+  fv2d::DevScalars *sc;
+  fv2d::DevScalars *sc_host; // pinned mirror for readbacks
+  double *stage_host;        // pinned staging row buffer for uploads/downloads (lazy)
+  size_t stage_bytes;
+
+  CUtensorMap tmapQ[2]; // TMA descriptors of Q[0], Q[1]
+  bool tmap_ok;
+  int acc_parity; // which inv_acc slot the NEXT sweep accumulates into
+
+  // multi-GPU peers (slab above / below)
+  double *peerQ_lo[2], *peerQ_hi[2]; // neighbour's Q[0], Q[1] (mapped through IPC / peer access)
+  fv2d::DevScalars *peer_sc[8];
+  void *ipc_opened[24];
+  int n_ipc_opened;
+  bool connected;
+};

@@ -1,0 +1,59 @@
+// fv2d_kernels.h — host-callable launchers implemented in fv2d_ops.cu / fv2d_sweep.cu.
+#pragma once
+
+#include "fv2d_common.cuh"
+
+namespace fv2d
+{
+
+// ---- operator-level kernels (fv2d_ops.cu, bit-exact reference order)
+void launch_fill_boundaries(const KParams &kp, double *Q, cudaStream_t s);
+void launch_fill_x_ghosts_of_halo_rows(const KParams &kp, double *Q, cudaStream_t s);
+void launch_prim_to_cons(const KParams &kp, const double *Q, double *U, cudaStream_t s);
+void launch_cons_to_prim(const KParams &kp, const double *U, double *Q, cudaStream_t s);
+void launch_check_negatives(const KParams &kp, double *Q, unsigned long long *counts, cudaStream_t s);
+void launch_compute_dt(const KParams &kp, const double *Q, unsigned long long *acc, cudaStream_t s);
+void launch_finalize_dt(const KParams &kp, const unsigned long long *acc, cudaStream_t s);
+void launch_compute_slopes(const KParams &kp, const double *Q, double *sX, double *sY, cudaStream_t s);
+void launch_fluxes_and_update(const KParams &kp, const double *Q, const double *sX, const double *sY, double *Unew,
+                              double dt, cudaStream_t s);
+void launch_thermal_conduction(const KParams &kp, const double *Q, double *Unew, double dt, cudaStream_t s);
+void launch_viscosity(const KParams &kp, const double *Q, double *Unew, double dt, cudaStream_t s);
+void launch_rk2_correct(const KParams &kp, const double *U0, double *Unew, cudaStream_t s);
+void launch_mass_energy(const KParams &kp, const double *U, double *rowsum, cudaStream_t s);
+
+// ---- fused hot path (fv2d_sweep.cu)
+
+// Step prologue: ghost fill of Q (composed x/y passes) + device-side clock bookkeeping.
+struct StepBeginArgs
+{
+  int use_device_dt; // 1: dt = CFL / max(inv_acc[acc_read]); 0: dt = dt_host
+  double dt_host;
+  int acc_read;  // inv_acc slot holding the maxima of the CURRENT state
+  int acc_reset; // inv_acc slot the coming sweep accumulates into (reset here)
+  int advance;   // 1: t += dt, step++, dt history (once per time step); 0: ghost fill only
+};
+void launch_step_begin(const KParams &kp, double *Q, const StepBeginArgs &a, cudaStream_t s);
+
+// One fused Runge-Kutta stage:  Uout = Uin + dt*L(Qin) [ ; Uout = 0.5*(U0 + Uout) ],
+// Qout = consToPrim(Uout) [ ; checkNegatives ; inverse-dt maxima of Qout ].
+struct SweepArgs
+{
+  KParams kp;
+  const double *Uin;
+  double *Uout;
+  const double *U0; // RK2 stage 2: the state at the start of the step; else nullptr
+  double *Qout;
+  int final_stage; // 1: checkNegatives + dt reduction of the new state
+  int acc_slot;    // inv_acc slot to atomically max into (final stage)
+  int chunk_rows;  // rows per CTA work item
+  int n_strips;
+};
+// tmapQ must describe the array the stage READS (Qin).  Returns cudaSuccess or the launch error;
+// sets *launches to the number of kernels enqueued.
+cudaError_t launch_sweep(const CUtensorMap &tmapQ, const SweepArgs &a, cudaStream_t s);
+// Opt-in dynamic shared memory etc.; call once per process before the first sweep.
+cudaError_t sweep_configure();
+int sweep_strip_width();
+
+} // namespace fv2d

@@ -1,0 +1,587 @@
+// fv2d_ops.cu — operator-level kernels: one kernel per reference operator, one thread per
+// cell, arithmetic in the reference's order.  Compiled with --fmad=false so that results
+// are bit-identical to the reference's Kokkos-OpenMP build (IEEE div/sqrt are correctly
+// rounded on both sides).  These back the operator-level C ABI (fv2d_update & friends),
+// the step-0 dt, and serve as the on-device cross-check of the fused sweep kernel.
+//
+// Kernels and the reference code they replace:
+//   k_fill_boundaries          BoundaryConditions.h:82-147  (x-pass then y-pass, composed)
+//   k_prim_to_cons/cons_to_prim SimInfo.h:576-600
+//   k_check_negatives          SimInfo.h:602-646
+//   k_compute_dt (+finalize)   ComputeDt.h:18-65
+//   k_compute_slopes           Update.h:59-91
+//   k_fluxes_and_update        Update.h:93-174
+//   k_thermal_conduction       ThermalConduction.h:36-108
+//   k_viscosity                Viscosity.h:27-119
+//   k_rk2_correct              Update.h:214-220
+#include "fv2d_kernels.h"
+#include "fv2d_physics.cuh"
+
+namespace fv2d
+{
+
+// ------------------------------------------------------------------ ghost fill
+
+// Source index of ghost index k for boundary type bc (domain [beg, end), N = end - beg).
+__device__ __forceinline__ int bc_source(int bc, int k, int beg, int end, int N)
+{
+  switch (bc)
+  {
+  case FV2D_BC_REFLECTING:
+    return 2 * (k < beg ? beg : end) - k - 1; // BoundaryConditions.h:25-38
+  case FV2D_BC_PERIODIC:
+    return k < beg ? k + N : k - N; // BoundaryConditions.h:53-68
+  default:
+    return k < beg ? beg : end - 1; // absorbing: BoundaryConditions.h:94-95, 124-125
+  }
+}
+
+// The reference fills x-ghosts of the domain rows, then y-ghosts over the full width
+// (reading the x-ghosts just written, so corners are defined).  Every ghost value is
+// therefore a (possibly sign-flipped) copy of ONE domain cell: ghost (i,j) <- domain
+// (sx(i), sy(j)), u negated if x is reflecting and i is a ghost column, v negated if y is
+// reflecting and j is a ghost row.  Negation is exact, so composing the two passes into one
+// launch is bit-identical and needs no ordering between threads.
+// Ghost rows on an EDGE_NEIGHBOUR side are left alone (the halo exchange owns them).
+__global__ void k_fill_boundaries(KParams kp, double *__restrict__ Q)
+{
+  const fv2d_device_params &p = kp.p;
+  const int Ng = p.Ng, Ntx = p.Ntx;
+  const long long n_y = 2LL * Ng * Ntx;       // y-ghost rows, full width
+  const long long n_x = 2LL * Ng * p.Ny;      // x-ghost columns of domain rows
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n_y + n_x)
+    return;
+
+  int i, j;
+  if (tid < n_y)
+  {
+    const int r = int(tid / Ntx);
+    i           = int(tid - (long long)r * Ntx);
+    j           = (r < Ng) ? r : p.jend + (r - Ng);
+  }
+  else
+  {
+    const long long t = tid - n_y;
+    const int r       = int(t / (2 * Ng));
+    const int c       = int(t - (long long)r * (2 * Ng));
+    j                 = p.jbeg + r;
+    i                 = (c < Ng) ? c : p.iend + (c - Ng);
+  }
+
+  int js = j, is = i;
+  bool flip_u = false, flip_v = false;
+  if (j < p.jbeg || j >= p.jend)
+  {
+    const int edge = (j < p.jbeg) ? kp.edge_lo : kp.edge_hi;
+    if (edge != EDGE_PHYSICAL)
+      return;
+    js     = bc_source(p.boundary_y, j, p.jbeg, p.jend, p.Ny);
+    flip_v = (p.boundary_y == FV2D_BC_REFLECTING);
+  }
+  if (i < p.ibeg || i >= p.iend)
+  {
+    is     = bc_source(p.boundary_x, i, p.ibeg, p.iend, p.Nx);
+    flip_u = (p.boundary_x == FV2D_BC_REFLECTING);
+  }
+  State q = load_state(Q, kp.L, is, js);
+  if (flip_u)
+    q.v[IU] *= -1.0;
+  if (flip_v)
+    q.v[IV] *= -1.0;
+  store_state(Q, kp.L, i, j, q);
+}
+
+// x-ghost columns of the halo rows received from a neighbouring slab (multi-GPU only): the
+// neighbour pushes the domain columns, the x boundary condition is applied locally.
+__global__ void k_fill_x_ghosts_of_halo_rows(KParams kp, double *__restrict__ Q)
+{
+  const fv2d_device_params &p = kp.p;
+  const int Ng  = p.Ng;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= 2 * Ng * 2 * Ng)
+    return;
+  const int r = tid / (2 * Ng), c = tid % (2 * Ng);
+  const int j = (r < Ng) ? r : p.jend + (r - Ng);
+  if (((j < p.jbeg) ? kp.edge_lo : kp.edge_hi) != EDGE_NEIGHBOUR)
+    return;
+  const int i  = (c < Ng) ? c : p.iend + (c - Ng);
+  const int is = bc_source(p.boundary_x, i, p.ibeg, p.iend, p.Nx);
+  State q      = load_state(Q, kp.L, is, j);
+  if (p.boundary_x == FV2D_BC_REFLECTING)
+    q.v[IU] *= -1.0;
+  store_state(Q, kp.L, i, j, q);
+}
+
+// ------------------------------------------------------------------ conversions, sanity
+
+__global__ void k_prim_to_cons(KParams kp, const double *__restrict__ Q, double *__restrict__ U)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= kp.p.Ntx || j >= kp.p.Nty)
+    return;
+  store_state(U, kp.L, i, j, prim_to_cons(load_state(Q, kp.L, i, j), kp.p.gamma0));
+}
+
+__global__ void k_cons_to_prim(KParams kp, const double *__restrict__ U, double *__restrict__ Q)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= kp.p.Ntx || j >= kp.p.Nty)
+    return;
+  store_state(Q, kp.L, i, j, cons_to_prim(load_state(U, kp.L, i, j), kp.p.gamma0));
+}
+
+__device__ __forceinline__ unsigned warp_sum_u32(unsigned v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void k_check_negatives(KParams kp, double *__restrict__ Q, unsigned long long *__restrict__ counts)
+{
+  const int i   = kp.p.ibeg + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j   = kp.p.jbeg + blockIdx.y * blockDim.y + threadIdx.y;
+  unsigned nd = 0, np = 0, nn = 0;
+  if (i < kp.p.iend && j < kp.p.jend)
+  {
+    const long long o = kp.L.at(0, i, j);
+    double r = Q[o + IR * kp.L.plane], pr = Q[o + IP * kp.L.plane];
+    if (r < 0)
+    {
+      r                       = kp.eps_reset;
+      Q[o + IR * kp.L.plane] = r;
+      nd++;
+    }
+    if (pr < 0)
+    {
+      pr                      = kp.eps_reset;
+      Q[o + IP * kp.L.plane] = pr;
+      np++;
+    }
+    nn += (r != r) + (pr != pr);
+    const double u = Q[o + IU * kp.L.plane], v = Q[o + IV * kp.L.plane];
+    nn += (u != u) + (v != v);
+  }
+  nd = warp_sum_u32(nd);
+  np = warp_sum_u32(np);
+  nn = warp_sum_u32(nn);
+  if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0)
+  {
+    if (nd)
+      atomicAdd(&counts[0], (unsigned long long)nd);
+    if (np)
+      atomicAdd(&counts[1], (unsigned long long)np);
+    if (nn)
+      atomicAdd(&counts[2], (unsigned long long)nn);
+  }
+}
+
+// ------------------------------------------------------------------ time step
+
+__device__ __forceinline__ double warp_max_f64(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__global__ void k_compute_dt(KParams kp, const double *__restrict__ Q, unsigned long long *__restrict__ acc)
+{
+  const fv2d_device_params &p = kp.p;
+  const int i = p.ibeg + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = p.jbeg + blockIdx.y * blockDim.y + threadIdx.y;
+  double hyp  = -1.7976931348623157e308;
+  if (i < p.iend && j < p.jend)
+  {
+    State q   = load_state(Q, kp.L, i, j);
+    double cs = speed_of_sound(q, p.gamma0);
+    hyp       = (cs + fabs(q.v[IU])) / p.dx + (cs + fabs(q.v[IV])) / p.dy; // ComputeDt.h:34
+  }
+  hyp = warp_max_f64(hyp);
+  __shared__ double smax[32];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if ((tid & 31) == 0)
+    smax[tid >> 5] = hyp;
+  __syncthreads();
+  if (tid < 32)
+  {
+    const int nw = (blockDim.x * blockDim.y + 31) >> 5;
+    double v     = tid < nw ? smax[tid] : -1.7976931348623157e308;
+    v            = warp_max_f64(v);
+    if (tid == 0)
+      atomicMax(&acc[0], encode_ordered(v));
+  }
+}
+
+// The parabolic limits are the same for every cell (constant kappa / mu): ComputeDt.h:36-44.
+__host__ __device__ inline void parabolic_inv_dt(const fv2d_device_params &p, double &tc, double &visc)
+{
+  tc = p.epsilon;
+  if (p.thermal_conductivity_active)
+    tc = fmax(2.0 * p.kappa / (p.dx * p.dx), 2.0 * p.kappa / (p.dy * p.dy));
+  visc = p.epsilon;
+  if (p.viscosity_active)
+    visc = fmax(2.0 * p.mu / (p.dx * p.dx), 2.0 * p.mu / (p.dy * p.dy));
+}
+
+// dt = CFL / max({hyp, tc, visc})  (ComputeDt.h:64)
+__global__ void k_finalize_dt(KParams kp, const unsigned long long *__restrict__ acc)
+{
+  double hyp = decode_ordered(acc[0]);
+  double tc, visc;
+  parabolic_inv_dt(kp.p, tc, visc);
+  double m = hyp;
+  if (m < tc)
+    m = tc;
+  if (m < visc)
+    m = visc;
+  kp.sc->inv_dt_last[0] = hyp;
+  kp.sc->inv_dt_last[1] = tc;
+  kp.sc->inv_dt_last[2] = visc;
+  kp.sc->dt             = kp.p.CFL / m;
+}
+
+// ------------------------------------------------------------------ hyperbolic update
+
+__global__ void k_compute_slopes(KParams kp, const double *__restrict__ Q, double *__restrict__ sX,
+                                 double *__restrict__ sY)
+{
+  const fv2d_device_params &p = kp.p;
+  const int i = p.ibeg - 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = p.jbeg - 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= p.iend + 1 || j >= p.jend + 1)
+    return;
+#pragma unroll
+  for (int f = 0; f < 4; ++f)
+  {
+    const long long o = kp.L.at(f, i, j);
+    const double c    = Q[o];
+    const double dL = c - Q[o - 1], dR = Q[o + 1] - c;
+    const double dU = c - Q[o - kp.L.pitch], dD = Q[o + kp.L.pitch] - c;
+    sX[o] = minmod(dL, dR);
+    sY[o] = minmod(dU, dD);
+  }
+}
+
+// reference Update.h:14-37; PCM_WB == PCM (Q3)
+__device__ __forceinline__ State reconstruct(const KParams &kp, const double *__restrict__ Q,
+                                             const double *__restrict__ slopes, int i, int j, double sign, int dir)
+{
+  State q = load_state(Q, kp.L, i, j);
+  if (kp.p.reconstruction == FV2D_PLM)
+  {
+    State s = load_state(slopes, kp.L, i, j);
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+      q.v[f] = q.v[f] + s.v[f] * sign * 0.5;
+  }
+  return swap_component(q, dir);
+}
+
+// reference Update.h:104-169
+__device__ __forceinline__ void update_along_dir(const KParams &kp, const double *__restrict__ Q,
+                                                 const double *__restrict__ sX, const double *__restrict__ sY,
+                                                 State &un, double dt, int i, int j, int dir)
+{
+  const fv2d_device_params &p = kp.p;
+  const double *slopes        = (dir == FV2D_IX ? sX : sY);
+  const int dxm = (dir == FV2D_IX ? -1 : 0), dxp = (dir == FV2D_IX ? 1 : 0);
+  const int dym = (dir == FV2D_IY ? -1 : 0), dyp = (dir == FV2D_IY ? 1 : 0);
+
+  State qCL = reconstruct(kp, Q, slopes, i, j, -1.0, dir);
+  State qCR = reconstruct(kp, Q, slopes, i, j, 1.0, dir);
+  State qL  = reconstruct(kp, Q, slopes, i + dxm, j + dym, 1.0, dir);
+  State qR  = reconstruct(kp, Q, slopes, i + dxp, j + dyp, -1.0, dir);
+
+  const double gdx = (dir == FV2D_IX ? p.gx * p.dx : p.gy * p.dy);
+
+  State fluxL, fluxR;
+  double poutL, poutR;
+  riemann(p.riemann_solver, qL, qCL, gdx, fluxL, poutL, p);
+  riemann(p.riemann_solver, qCR, qR, gdx, fluxR, poutR, p);
+  fluxL = swap_component(fluxL, dir);
+  fluxR = swap_component(fluxR, dir);
+
+  const double rho = Q[kp.L.at(IR, i, j)];
+  // Update.h:148-156; only at the GLOBAL y boundary
+  if (p.well_balanced_flux_at_y_bc && dir == FV2D_IY)
+  {
+    const bool lo = (j == p.jbeg) && kp.edge_lo == EDGE_PHYSICAL;
+    const bool hi = (j == p.jend - 1) && kp.edge_hi == EDGE_PHYSICAL;
+    if (lo || hi)
+    {
+      const double g = get_gravity(kp, j, dir);
+      State f;
+      f.v[0] = 0.0, f.v[1] = 0.0, f.v[3] = 0.0;
+      if (lo)
+      {
+        f.v[2] = poutR - rho * g * p.dy;
+        fluxL  = f;
+      }
+      else
+      {
+        f.v[2] = poutL + rho * g * p.dy;
+        fluxR  = f;
+      }
+    }
+  }
+
+  const double delta = (dir == FV2D_IX ? p.dx : p.dy);
+#pragma unroll
+  for (int f = 0; f < 4; ++f)
+    un.v[f] += ((fluxL.v[f] - fluxR.v[f]) * dt) / delta; // Update.h:158-159
+
+  if (p.gravity_mode != FV2D_GRAV_NONE) // Update.h:161-166 (always into IV: Q4)
+  {
+    const double g = get_gravity(kp, j, dir);
+    un.v[IV] += dt * rho * g;
+    un.v[IE] += dt * 0.5 * (fluxL.v[IR] + fluxR.v[IR]) * g;
+  }
+}
+
+__global__ void k_fluxes_and_update(KParams kp, const double *__restrict__ Q, const double *__restrict__ sX,
+                                    const double *__restrict__ sY, double *__restrict__ Unew, double dt)
+{
+  const int i = kp.p.ibeg + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = kp.p.jbeg + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= kp.p.iend || j >= kp.p.jend)
+    return;
+  State un = load_state(Unew, kp.L, i, j);
+  update_along_dir(kp, Q, sX, sY, un, dt, i, j, FV2D_IX);
+  update_along_dir(kp, Q, sX, sY, un, dt, i, j, FV2D_IY);
+  store_state(Unew, kp.L, i, j, un);
+}
+
+// ------------------------------------------------------------------ thermal conduction
+
+__global__ void k_thermal_conduction(KParams kp, const double *__restrict__ Q, double *__restrict__ Unew, double dt)
+{
+  const fv2d_device_params &p = kp.p;
+  const int i = p.ibeg + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = p.jbeg + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= p.iend || j >= p.jend)
+    return;
+  const double dx = p.dx, dy = p.dy;
+  const double kappaL = 0.5 * (p.kappa + p.kappa), kappaR = kappaL, kappaU = kappaL, kappaD = kappaL;
+
+  const long long oR = kp.L.at(IR, i, j), oP = kp.L.at(IP, i, j);
+  const int pt = kp.L.pitch;
+  const double TC = Q[oP] / Q[oR];
+  const double TL = Q[oP - 1] / Q[oR - 1];
+  const double TR = Q[oP + 1] / Q[oR + 1];
+  const double TU = Q[oP - pt] / Q[oR - pt];
+  const double TD = Q[oP + pt] / Q[oR + pt];
+
+  double FL = kappaL * (TC - TL) / dx;
+  double FR = kappaR * (TR - TC) / dx;
+  double FU = kappaU * (TC - TU) / dy;
+  double FD = kappaD * (TD - TC) / dy;
+
+  // ThermalConduction.h:75-103: the y-boundary overrides replace FL / FR (Q7a)
+  if (j == p.jbeg && kp.edge_lo == EDGE_PHYSICAL && p.bctc_ymin != FV2D_BCTC_NONE)
+  {
+    if (p.bctc_ymin == FV2D_BCTC_FIXED_TEMPERATURE)
+      FL = kappaL * 2.0 * (TC - p.bctc_ymin_value) / dy;
+    else if (p.bctc_ymin == FV2D_BCTC_FIXED_GRADIENT)
+      FL = kappaL * p.bctc_ymin_value;
+  }
+  if (j == p.jend - 1 && kp.edge_hi == EDGE_PHYSICAL && p.bctc_ymax != FV2D_BCTC_NONE)
+  {
+    if (p.bctc_ymax == FV2D_BCTC_FIXED_TEMPERATURE)
+      FR = kappaR * 2.0 * (p.bctc_ymax_value - TC) / dy;
+    else if (p.bctc_ymax == FV2D_BCTC_FIXED_GRADIENT)
+      FR = kappaR * p.bctc_ymax_value;
+  }
+
+  Unew[kp.L.at(IE, i, j)] += dt / dx * (FR - FL) + dt / dy * (FD - FU);
+}
+
+// ------------------------------------------------------------------ viscosity
+
+__global__ void k_viscosity(KParams kp, const double *__restrict__ Q, double *__restrict__ Unew, double dt)
+{
+  const fv2d_device_params &p = kp.p;
+  const int i = p.ibeg + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = p.jbeg + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= p.iend || j >= p.jend)
+    return;
+  const double four_thirds = 4.0 / 3.0, two_thirds = 2.0 / 3.0;
+  const double one_over_dx = 1.0 / p.dx, one_over_dy = 1.0 / p.dy;
+  const double mu = p.mu;
+
+  // stencil[dj+1][di+1] = Q(i+di, j+dj), u and v only
+  double su[3][3], sv[3][3];
+#pragma unroll
+  for (int dj = -1; dj < 2; ++dj)
+#pragma unroll
+    for (int di = -1; di < 2; ++di)
+    {
+      su[dj + 1][di + 1] = Q[kp.L.at(IU, i + di, j + dj)];
+      sv[dj + 1][di + 1] = Q[kp.L.at(IV, i + di, j + dj)];
+    }
+
+  double fx[4] = {0.0, 0.0, 0.0, 0.0}, fy[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int side = 1; side < 3; ++side)
+  {
+    const double sign = (side == 1 ? -1.0 : 1.0);
+    {
+      const double qiU = 0.5 * (su[1][side] + su[1][side - 1]);
+      const double qiV = 0.5 * (sv[1][side] + sv[1][side - 1]);
+      const double dudx = one_over_dx * (su[1][side] - su[1][side - 1]);
+      const double dvdx = one_over_dx * (sv[1][side] - sv[1][side - 1]);
+      const double dudy = 0.25 * one_over_dy * (su[2][side] - su[0][side] + su[2][side - 1] - su[0][side - 1]);
+      const double dvdy = 0.25 * one_over_dy * (sv[2][side] - sv[0][side] + sv[2][side - 1] - sv[0][side - 1]);
+      const double tau_xx = four_thirds * dudx - two_thirds * dvdy;
+      const double tau_xy = dvdx + dudy;
+      fx[IU] += sign * mu * tau_xx;
+      fx[IV] += sign * mu * tau_xy;
+      fx[IE] += sign * mu * (tau_xx * qiU + tau_xy * qiV);
+    }
+    {
+      const double qiU = 0.5 * (su[side][1] + su[side - 1][1]);
+      const double qiV = 0.5 * (sv[side][1] + sv[side - 1][1]);
+      const double dudy = one_over_dy * (su[side][1] - su[side - 1][1]);
+      const double dvdy = one_over_dy * (sv[side][1] - sv[side - 1][1]);
+      const double dudx = 0.25 * one_over_dx * (su[side][2] - su[side][0] + su[side - 1][2] - su[side - 1][0]);
+      const double dvdx = 0.25 * one_over_dx * (sv[side][2] - sv[side][0] + sv[side - 1][2] - sv[side - 1][0]);
+      const double tau_yy = four_thirds * dvdy - two_thirds * dudx;
+      const double tau_xy = dvdx + dudy;
+      fy[IU] += sign * mu * tau_xy;
+      fy[IV] += sign * mu * tau_yy;
+      fy[IE] += sign * mu * (tau_xy * qiU + tau_yy * qiV);
+    }
+  }
+  // Viscosity.h:115-117 (no division by the cell size: Q8)
+  State un = load_state(Unew, kp.L, i, j);
+#pragma unroll
+  for (int f = 0; f < 4; ++f)
+    un.v[f] += (fx[f] + fy[f]) * dt;
+  store_state(Unew, kp.L, i, j, un);
+}
+
+// ------------------------------------------------------------------ RK2 combine, sums
+
+__global__ void k_rk2_correct(KParams kp, const double *__restrict__ U0, double *__restrict__ Unew)
+{
+  const int i = kp.p.ibeg + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = kp.p.jbeg + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= kp.p.iend || j >= kp.p.jend)
+    return;
+#pragma unroll
+  for (int f = 0; f < 4; ++f)
+  {
+    const long long o = kp.L.at(f, i, j);
+    Unew[o]           = 0.5 * (U0[o] + Unew[o]);
+  }
+}
+
+// Deterministic two-level sum of U[f]*dx*dy over the domain: per-row partials (fixed order
+// inside a row block), then a single thread adds the rows in order.
+__global__ void k_row_sums(KParams kp, const double *__restrict__ U, double *__restrict__ rowsum)
+{
+  const int j = kp.p.jbeg + blockIdx.x;
+  __shared__ double sm[2][256];
+  double m = 0.0, e = 0.0;
+  for (int i = kp.p.ibeg + threadIdx.x; i < kp.p.iend; i += blockDim.x)
+  {
+    m += U[kp.L.at(IR, i, j)];
+    e += U[kp.L.at(IE, i, j)];
+  }
+  sm[0][threadIdx.x] = m;
+  sm[1][threadIdx.x] = e;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1)
+  {
+    if (threadIdx.x < s)
+    {
+      sm[0][threadIdx.x] += sm[0][threadIdx.x + s];
+      sm[1][threadIdx.x] += sm[1][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+  {
+    rowsum[2 * blockIdx.x]     = sm[0][0];
+    rowsum[2 * blockIdx.x + 1] = sm[1][0];
+  }
+}
+__global__ void k_final_sums(KParams kp, const double *__restrict__ rowsum)
+{
+  double m = 0.0, e = 0.0;
+  for (int r = 0; r < kp.p.Ny; ++r)
+  {
+    m += rowsum[2 * r];
+    e += rowsum[2 * r + 1];
+  }
+  kp.sc->sums[0] = m * kp.p.dx * kp.p.dy;
+  kp.sc->sums[1] = e * kp.p.dx * kp.p.dy;
+}
+
+// ------------------------------------------------------------------ launchers
+
+static inline dim3 grid2d(int nx, int ny, dim3 b) { return dim3((nx + b.x - 1) / b.x, (ny + b.y - 1) / b.y); }
+static const dim3 kBlk(64, 4);
+
+void launch_fill_boundaries(const KParams &kp, double *Q, cudaStream_t s)
+{
+  const long long n = 2LL * kp.p.Ng * kp.p.Ntx + 2LL * kp.p.Ng * kp.p.Ny;
+  k_fill_boundaries<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(kp, Q);
+}
+void launch_fill_x_ghosts_of_halo_rows(const KParams &kp, double *Q, cudaStream_t s)
+{
+  k_fill_x_ghosts_of_halo_rows<<<1, 64, 0, s>>>(kp, Q);
+}
+void launch_prim_to_cons(const KParams &kp, const double *Q, double *U, cudaStream_t s)
+{
+  k_prim_to_cons<<<grid2d(kp.p.Ntx, kp.p.Nty, kBlk), kBlk, 0, s>>>(kp, Q, U);
+}
+void launch_cons_to_prim(const KParams &kp, const double *U, double *Q, cudaStream_t s)
+{
+  k_cons_to_prim<<<grid2d(kp.p.Ntx, kp.p.Nty, kBlk), kBlk, 0, s>>>(kp, U, Q);
+}
+void launch_check_negatives(const KParams &kp, double *Q, unsigned long long *counts, cudaStream_t s)
+{
+  k_check_negatives<<<grid2d(kp.p.Nx, kp.p.Ny, kBlk), kBlk, 0, s>>>(kp, Q, counts);
+}
+void launch_compute_dt(const KParams &kp, const double *Q, unsigned long long *acc, cudaStream_t s)
+{
+  k_compute_dt<<<grid2d(kp.p.Nx, kp.p.Ny, kBlk), kBlk, 0, s>>>(kp, Q, acc);
+}
+void launch_finalize_dt(const KParams &kp, const unsigned long long *acc, cudaStream_t s)
+{
+  k_finalize_dt<<<1, 1, 0, s>>>(kp, acc);
+}
+void launch_compute_slopes(const KParams &kp, const double *Q, double *sX, double *sY, cudaStream_t s)
+{
+  k_compute_slopes<<<grid2d(kp.p.Nx + 2, kp.p.Ny + 2, kBlk), kBlk, 0, s>>>(kp, Q, sX, sY);
+}
+void launch_fluxes_and_update(const KParams &kp, const double *Q, const double *sX, const double *sY, double *Unew,
+                              double dt, cudaStream_t s)
+{
+  k_fluxes_and_update<<<grid2d(kp.p.Nx, kp.p.Ny, kBlk), kBlk, 0, s>>>(kp, Q, sX, sY, Unew, dt);
+}
+void launch_thermal_conduction(const KParams &kp, const double *Q, double *Unew, double dt, cudaStream_t s)
+{
+  k_thermal_conduction<<<grid2d(kp.p.Nx, kp.p.Ny, kBlk), kBlk, 0, s>>>(kp, Q, Unew, dt);
+}
+void launch_viscosity(const KParams &kp, const double *Q, double *Unew, double dt, cudaStream_t s)
+{
+  k_viscosity<<<grid2d(kp.p.Nx, kp.p.Ny, kBlk), kBlk, 0, s>>>(kp, Q, Unew, dt);
+}
+void launch_rk2_correct(const KParams &kp, const double *U0, double *Unew, cudaStream_t s)
+{
+  k_rk2_correct<<<grid2d(kp.p.Nx, kp.p.Ny, kBlk), kBlk, 0, s>>>(kp, U0, Unew);
+}
+void launch_mass_energy(const KParams &kp, const double *U, double *rowsum, cudaStream_t s)
+{
+  k_row_sums<<<kp.p.Ny, 256, 0, s>>>(kp, U, rowsum);
+  k_final_sums<<<1, 1, 0, s>>>(kp, rowsum);
+}
+
+} // namespace fv2d

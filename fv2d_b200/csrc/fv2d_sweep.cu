@@ -1,0 +1,863 @@
+// fv2d_sweep.cu — the fused hot path: one sm_100a kernel per Runge-Kutta stage.
+//
+// Replaces, in ONE pass over memory, the reference's per-stage kernel chain
+//   computeSlopes (Update.h:59-91) -> computeFluxesAndUpdate (Update.h:93-174)
+//   -> applyThermalConduction (ThermalConduction.h:36-108) -> applyViscosity
+//   (Viscosity.h:27-119) -> [RK2 correct, Update.h:214-220] -> consToPrim
+//   (SimInfo.h:576-587) -> checkNegatives (SimInfo.h:602-646) -> computeDt of the new
+//   state (ComputeDt.h:18-65)
+// Algorithmic traffic: read Q^n + U^n, write U^{n+1} + Q^{n+1} = 128 B per cell.
+//
+// Work decomposition ("column sweep"): the domain is cut into strips of W = NT-4 columns
+// and chunks of `chunk_rows` rows; one CTA of NT threads owns one (strip, chunk).  Thread t
+// owns column i0-2+t of the strip (2 halo columns each side) and marches through the rows:
+//   * Q rows (primitive SoA tile row + its 2-cell x halo, 4 fields) are staged into a
+//     shared-memory ring by TMA (one cp.async.bulk.tensor.3d box of NT x 1 x 4 doubles per
+//     row, completion on an mbarrier), NS rows deep, so HBM latency is hidden without
+//     spending registers on in-flight loads;
+//   * the y-direction stencil lives in registers (each thread keeps the rolling
+//     q(j), q(j+1), the reconstructed +y face state and the y-face flux of its column): every
+//     y-face flux is computed exactly once;
+//   * the x-direction needs the neighbour columns: slopes read q(i+-1) from the ring, the
+//     reconstructed +x face state (and its sound speed) and the x-face flux are exchanged
+//     through small double-buffered shared arrays with ONE __syncthreads per row: every
+//     x-face flux is computed exactly once (by the thread on its right);
+//   * each slope, each face state, each sound speed is computed once per cell; divisions
+//     and square roots are MUFU seeds + Newton/Goldschmidt steps (no IEEE slow paths);
+//   * the epilogue of a row writes U^{n+1}, converts to primitives, applies the
+//     negative-density/pressure reset, accumulates the CFL maximum, writes Q^{n+1}.
+// The per-CTA CFL maximum goes to a device scalar with one atomicMax: the next dt never
+// leaves the GPU.
+#include "fv2d_kernels.h"
+
+#include <cstring>
+
+namespace fv2d
+{
+
+// --------------------------------------------------------------------------- PTX helpers
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "WAIT_LOOP:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra WAIT_DONE;\n"
+               "bra WAIT_LOOP;\n"
+               "WAIT_DONE:\n"
+               "}\n" ::"r"(smem_u32(bar)),
+               "r"(parity)
+               : "memory");
+}
+// TMA: global (3-D tensor map: column, row, field) -> shared, completion on mbarrier
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, int x, int y, int z, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// 1/a: MUFU.RCP64H seed (>= 20 bits) + two Newton steps -> ~1 ulp, no slow path
+__device__ __forceinline__ double frcp(double a)
+{
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double e = fma(-a, y, 1.0);
+  y        = fma(y, e, y);
+  e        = fma(-a, y, 1.0);
+  y        = fma(y, e, y);
+  return y;
+}
+// sound speed sqrt(gp / rho) with gp = gamma0 * P: c = gp * rsqrt(gp * rho);
+// MUFU.RSQ64H seed + two coupled (Goldschmidt) steps
+__device__ __forceinline__ double csound(double gp, double rho)
+{
+  const double y = gp * rho;
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+  double g = y * r;   // ~ sqrt(y)
+  double h = 0.5 * r; // ~ 1 / (2 sqrt(y))
+  double e = fma(-g, h, 0.5);
+  g        = fma(g, e, g);
+  h        = fma(h, e, h);
+  e        = fma(-g, h, 0.5);
+  h        = fma(h, e, h);
+  return (gp + gp) * h;
+}
+
+// minmod (Update.h:69-85), branch-free
+__device__ __forceinline__ double minmod_f(double dL, double dR)
+{
+  const double r = (fabs(dL) < fabs(dR)) ? dL : dR;
+  return (dL * dR < 0.0) ? 0.0 : r;
+}
+
+// A face state in the frame of the face normal: n = normal velocity, t = tangential.
+struct FaceState
+{
+  double r, n, t, p, c;
+};
+// A face flux in the same frame: mass, normal momentum, tangential momentum, energy.
+struct FaceFlux
+{
+  double m, n, t, e, pout;
+};
+
+// HLLC (RiemannSolvers.h:53-128), re-associated: one reciprocal for 1/(rcL+rcR), one for
+// the star state of the side that is actually taken; same branch structure:
+//   SL > 0 -> left state; else uS > 0 -> left star; else SR > 0 -> right star; else right.
+__device__ __forceinline__ FaceFlux hllc_f(const FaceState &L, const FaceState &R, double entho)
+{
+  const double cmax = fmax(L.c, R.c);
+  const double SL   = fmin(L.n, R.n) - cmax;
+  const double SR   = fmax(L.n, R.n) + cmax;
+
+  const double rcL = L.r * (L.n - SL);
+  const double rcR = R.r * (SR - R.n);
+  const double inv = frcp(rcR + rcL);
+  const double uS  = (rcR * R.n + rcL * L.n + (L.p - R.p)) * inv;
+  const double pS  = (rcR * L.p + rcL * R.p + rcL * rcR * (L.n - R.n)) * inv;
+
+  const bool left = (SL > 0.0) || (uS > 0.0);
+  const bool star = left ? !(SL > 0.0) : (SR > 0.0);
+
+  const double rK = left ? L.r : R.r;
+  const double uK = left ? L.n : R.n;
+  const double vK = left ? L.t : R.t;
+  const double pK = left ? L.p : R.p;
+  const double SK = left ? SL : SR;
+
+  const double EK = 0.5 * rK * (uK * uK + vK * vK) + pK * entho;
+  const double d  = frcp(SK - uS);
+  const double w  = SK - uK;
+  const double rS = rK * w * d;
+  const double ES = (w * EK - pK * uK + pS * uS) * d;
+
+  const double r = star ? rS : rK;
+  const double u = star ? uS : uK;
+  const double p = star ? pS : pK;
+  const double E = star ? ES : EK;
+
+  FaceFlux f;
+  f.m    = r * u;
+  f.n    = fma(f.m, u, p);
+  f.t    = f.m * vK;
+  f.e    = (E + p) * u;
+  f.pout = p;
+  return f;
+}
+
+// HLL with Davis speeds (RiemannSolvers.h:7-51)
+__device__ __forceinline__ FaceFlux hll_f(const FaceState &L, const FaceState &R, double entho)
+{
+  const double SL = fmin(L.n - L.c, R.n - R.c);
+  const double SR = fmax(L.n + L.c, R.n + R.c);
+
+  const double mL = L.r * L.n, mR = R.r * R.n;
+  const double EL = 0.5 * L.r * (L.n * L.n + L.t * L.t) + L.p * entho;
+  const double ER = 0.5 * R.r * (R.n * R.n + R.t * R.t) + R.p * entho;
+  const double FLm = mL, FLn = fma(mL, L.n, L.p), FLt = mL * L.t, FLe = (L.p + EL) * L.n;
+  const double FRm = mR, FRn = fma(mR, R.n, R.p), FRt = mR * R.t, FRe = (R.p + ER) * R.n;
+
+  const double inv = frcp(SR - SL);
+  const double ss  = SL * SR;
+  FaceFlux f;
+  f.m    = ((SR * FLm - SL * FRm) + ss * (R.r - L.r)) * inv;
+  f.n    = ((SR * FLn - SL * FRn) + ss * (mR - mL)) * inv;
+  f.t    = ((SR * FLt - SL * FRt) + ss * (R.r * R.t - L.r * L.t)) * inv;
+  f.e    = ((SR * FLe - SL * FRe) + ss * (ER - EL)) * inv;
+  f.pout = 0.5 * (L.p + R.p);
+  if (SL >= 0.0)
+  {
+    f.m = FLm, f.n = FLn, f.t = FLt, f.e = FLe, f.pout = L.p;
+  }
+  else if (SR <= 0.0)
+  {
+    f.m = FRm, f.n = FRn, f.t = FRt, f.e = FRe, f.pout = R.p;
+  }
+  return f;
+}
+
+// FSLP (RiemannSolvers.h:137-171)
+__device__ __forceinline__ FaceFlux fslp_f(const FaceState &L, const FaceState &R, double entho, double gdx, double K)
+{
+  const double ai    = K * fmax(L.r * L.c, R.r * R.c);
+  const double theta = fmin(1.0, fmax(fabs(L.n) * frcp(L.c), fabs(R.n) * frcp(R.c)));
+  const double ustar = 0.5 * (R.n + L.n) - 0.5 * frcp(ai) * (R.p - L.p - 0.5 * (L.r + R.r) * gdx);
+  const double Pi    = 0.5 * (R.p + L.p) - theta * 0.5 * ai * (R.n - L.n);
+  const bool up      = ustar > 0.0;
+  const double r = up ? L.r : R.r, n = up ? L.n : R.n, t = up ? L.t : R.t, p = up ? L.p : R.p;
+  const double E = 0.5 * r * (n * n + t * t) + p * entho;
+  FaceFlux f;
+  f.m    = ustar * r;
+  f.n    = fma(f.m, n, Pi);
+  f.t    = f.m * t;
+  f.e    = ustar * (E + Pi);
+  f.pout = Pi;
+  return f;
+}
+
+template <int SOLVER>
+__device__ __forceinline__ FaceFlux riemann_f(const FaceState &L, const FaceState &R, double entho, double gdx, double K)
+{
+  if constexpr (SOLVER == FV2D_HLL)
+    return hll_f(L, R, entho);
+  else if constexpr (SOLVER == FV2D_FSLP)
+    return fslp_f(L, R, entho, gdx, K);
+  else
+    return hllc_f(L, R, entho);
+}
+
+// --------------------------------------------------------------------------- the kernel
+
+constexpr int kNS = 8; // ring depth in rows
+
+template <int NT>
+struct SweepSmem
+{
+  double ring[kNS][4][NT]; // TMA destination: [slot][field][column]
+  double X1[2][5][NT];     // +x face state (r,u,v,p,c) of each column, by row parity
+  double X2[2][4][NT];     // x-face flux (m,n,t,e) at the LEFT face of each column, by row parity
+  uint64_t full[kNS];      // TMA completion barriers
+};
+
+template <int NT, bool PLM, int SOLVER, bool GRAV, bool DIFF>
+__global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : 2))
+k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepArgs a)
+{
+  constexpr int W = NT - 4;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SweepSmem<NT> &S = *reinterpret_cast<SweepSmem<NT> *>(smem_raw);
+
+  const fv2d_device_params &p = a.kp.p;
+  const Layout &L             = a.kp.L;
+
+  const int t     = threadIdx.x;
+  const int strip = blockIdx.x;
+  const int i0    = p.ibeg + strip * W; // first interior column of the strip
+  const int col   = i0 - 2 + t;         // this thread's column
+  const int j0    = p.jbeg + blockIdx.y * a.chunk_rows;
+  const int j1    = min(j0 + a.chunk_rows, p.jend); // rows [j0, j1) are updated
+  const int rbase = j0 - 2;                         // first row staged
+  const int rlast = j1 + 1;                         // last row staged
+  const bool interior = (t >= 2) && (t < NT - 2) && (col < p.iend);
+  const int tl = (t > 0 ? t - 1 : 0), tr = (t < NT - 1 ? t + 1 : NT - 1);
+
+  const double dt    = a.kp.sc->dt;
+  const double dtdx  = dt / p.dx;
+  const double dtdy  = dt / p.dy;
+  const double gamma = p.gamma0;
+  const double gm1   = gamma - 1.0;
+  const double entho = 1.0 / gm1;
+
+  if (t == 0)
+  {
+#pragma unroll
+    for (int s = 0; s < kNS; ++s)
+      mbar_init(&S.full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  constexpr uint32_t kRowBytes = 4u * NT * sizeof(double);
+  const int tma_x              = L.lead + i0 - 2;
+  if (t == 0)
+  {
+    for (int r = rbase; r <= min(rlast, rbase + kNS - 1); ++r)
+    {
+      const int s = r - rbase;
+      mbar_expect_tx(&S.full[s], kRowBytes);
+      tma_load_3d(&S.ring[s][0][0], &tmQ, tma_x, r, 0, &S.full[s]);
+    }
+  }
+
+  auto slot_of  = [&](int r) { return (r - rbase) & (kNS - 1); };
+  auto wait_row = [&](int r) { mbar_wait(&S.full[slot_of(r)], (uint32_t)(((r - rbase) / kNS) & 1)); };
+
+  // ---- pre-prologue: rows j0-2, j0-1, j0 of this column
+  double qk[4], qn[4]; // q(row k), q(row k+1)
+  FaceState yp;        // +y face state of row k (frame of the y normal: n = v, t = u)
+  wait_row(rbase);
+  wait_row(rbase + 1);
+  wait_row(rbase + 2);
+  {
+    double qa[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+    {
+      qa[f] = S.ring[slot_of(rbase)][f][t];
+      qk[f] = S.ring[slot_of(rbase + 1)][f][t];
+      qn[f] = S.ring[slot_of(rbase + 2)][f][t];
+    }
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    if constexpr (PLM)
+    {
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+        s[f] = minmod_f(qk[f] - qa[f], qn[f] - qk[f]);
+    }
+    yp.r = fma(0.5, s[0], qk[0]);
+    yp.t = fma(0.5, s[1], qk[1]);
+    yp.n = fma(0.5, s[2], qk[2]);
+    yp.p = fma(0.5, s[3], qk[3]);
+    yp.c = csound(gamma * yp.p, yp.r);
+  }
+
+  FaceFlux fy_lo;  // y-face flux below row k+... (becomes the low face of the next row)
+  FaceState xm;    // -x face state of row k (own cell, left face), frame of the x normal
+  double rho_k = qk[0];
+  fy_lo.m = fy_lo.n = fy_lo.t = fy_lo.e = fy_lo.pout = 0.0;
+  xm.r = xm.n = xm.t = xm.p = xm.c = 0.0;
+
+  // U prefetch (row j0), own column, straight from global memory (coalesced, read once)
+  double un[4] = {0.0, 0.0, 0.0, 0.0};
+  const long long ocol = L.at(0, col, 0);
+  if (interior)
+  {
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+      un[f] = a.Uin[ocol + f * L.plane + (long long)j0 * L.pitch];
+  }
+
+  double inv_dt_max = -1.7976931348623157e308;
+  unsigned n_negr = 0, n_negp = 0, n_nan = 0;
+
+  // ---- march: iteration k finishes row k; k = j0-1 is the warm-up (no update)
+  for (int k = j0 - 1; k < j1; ++k)
+  {
+    const int par = k & 1;
+    // A. new row k+2 enters; y slopes / face states of row k+1; y-face flux at k+1/2
+    wait_row(k + 2);
+    double qnn[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+      qnn[f] = S.ring[slot_of(k + 2)][f][t];
+
+    FaceState ym, yp1;
+    {
+      double s[4] = {0.0, 0.0, 0.0, 0.0};
+      if constexpr (PLM)
+      {
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+          s[f] = minmod_f(qn[f] - qk[f], qnn[f] - qn[f]);
+      }
+      ym.r  = fma(-0.5, s[0], qn[0]);
+      ym.t  = fma(-0.5, s[1], qn[1]);
+      ym.n  = fma(-0.5, s[2], qn[2]);
+      ym.p  = fma(-0.5, s[3], qn[3]);
+      yp1.r = fma(0.5, s[0], qn[0]);
+      yp1.t = fma(0.5, s[1], qn[1]);
+      yp1.n = fma(0.5, s[2], qn[2]);
+      yp1.p = fma(0.5, s[3], qn[3]);
+      if constexpr (PLM)
+      {
+        ym.c  = csound(gamma * ym.p, ym.r);
+        yp1.c = csound(gamma * yp1.p, yp1.r);
+      }
+      else
+      {
+        ym.c  = csound(gamma * ym.p, ym.r);
+        yp1.c = ym.c;
+      }
+    }
+    const double gdy = p.gy * p.dy, gdx = p.gx * p.dx;
+    FaceFlux fy_hi = riemann_f<SOLVER>(yp, ym, entho, gdy, p.fslp_K);
+
+    // B. x-face flux at the left face of (col, k): left state from the neighbour thread
+    if (k >= j0)
+    {
+      FaceState xl;
+      xl.r = S.X1[par][0][tl];
+      xl.n = S.X1[par][1][tl];
+      xl.t = S.X1[par][2][tl];
+      xl.p = S.X1[par][3][tl];
+      xl.c = S.X1[par][4][tl];
+      FaceFlux fx = riemann_f<SOLVER>(xl, xm, entho, gdx, p.fslp_K);
+      S.X2[par][0][t] = fx.m;
+      S.X2[par][1][t] = fx.n;
+      S.X2[par][2][t] = fx.t;
+      S.X2[par][3][t] = fx.e;
+    }
+
+    // C. x slopes / face states of row k+1 (published for the neighbour on the right)
+    FaceState xm1;
+    {
+      const int sl = slot_of(k + 1);
+      double s[4]  = {0.0, 0.0, 0.0, 0.0};
+      if constexpr (PLM)
+      {
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+          s[f] = minmod_f(qn[f] - S.ring[sl][f][tl], S.ring[sl][f][tr] - qn[f]);
+      }
+      xm1.r = fma(-0.5, s[0], qn[0]);
+      xm1.n = fma(-0.5, s[1], qn[1]);
+      xm1.t = fma(-0.5, s[2], qn[2]);
+      xm1.p = fma(-0.5, s[3], qn[3]);
+      FaceState xp1;
+      xp1.r = fma(0.5, s[0], qn[0]);
+      xp1.n = fma(0.5, s[1], qn[1]);
+      xp1.t = fma(0.5, s[2], qn[2]);
+      xp1.p = fma(0.5, s[3], qn[3]);
+      if constexpr (PLM)
+      {
+        xm1.c = csound(gamma * xm1.p, xm1.r);
+        xp1.c = csound(gamma * xp1.p, xp1.r);
+      }
+      else
+      {
+        xm1.c = ym.c; // PCM: one sound speed per cell
+        xp1.c = ym.c;
+      }
+      S.X1[par ^ 1][0][t] = xp1.r;
+      S.X1[par ^ 1][1][t] = xp1.n;
+      S.X1[par ^ 1][2][t] = xp1.t;
+      S.X1[par ^ 1][3][t] = xp1.p;
+      S.X1[par ^ 1][4][t] = xp1.c;
+    }
+
+    __syncthreads();
+
+    // E. refill the ring slot of row k-2 (no thread reads it any more) with row k-2+NS
+    if (t == 0)
+    {
+      const int rnew = k - 2 + kNS;
+      if (k - 2 >= rbase && rnew <= rlast)
+      {
+        const int s = slot_of(rnew);
+        mbar_expect_tx(&S.full[s], kRowBytes);
+        tma_load_3d(&S.ring[s][0][0], &tmQ, tma_x, rnew, 0, &S.full[s]);
+      }
+    }
+
+    // D. finish row k
+    if (k >= j0)
+    {
+      // next row's U: issue the loads now, consume them next iteration
+      double un_next[4] = {0.0, 0.0, 0.0, 0.0};
+      if (interior && k + 1 < j1)
+      {
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+          un_next[f] = a.Uin[ocol + f * L.plane + (long long)(k + 1) * L.pitch];
+      }
+
+      FaceFlux fxr;
+      fxr.m = S.X2[par][0][tr];
+      fxr.n = S.X2[par][1][tr];
+      fxr.t = S.X2[par][2][tr];
+      fxr.e = S.X2[par][3][tr];
+      FaceFlux fxl;
+      fxl.m = S.X2[par][0][t];
+      fxl.n = S.X2[par][1][t];
+      fxl.t = S.X2[par][2][t];
+      fxl.e = S.X2[par][3][t];
+
+      // y fluxes back in the grid frame: (m, t, n, e) -> (rho, rho u, rho v, E)
+      double fyl[4] = {fy_lo.m, fy_lo.t, fy_lo.n, fy_lo.e};
+      double fyh[4] = {fy_hi.m, fy_hi.t, fy_hi.n, fy_hi.e};
+
+      double gyv = 0.0, gxv = 0.0;
+      if constexpr (GRAV)
+      {
+        gxv = (p.gravity_mode == FV2D_GRAV_CONSTANT) ? p.gx : a.kp.gtab[k];
+        gyv = (p.gravity_mode == FV2D_GRAV_CONSTANT) ? p.gy : a.kp.gtab[k];
+        // well-balanced flux at the global y boundary (Update.h:148-156)
+        if (p.well_balanced_flux_at_y_bc)
+        {
+          if (k == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL)
+          {
+            fyl[0] = 0.0, fyl[1] = 0.0, fyl[3] = 0.0;
+            fyl[2] = fy_hi.pout - rho_k * gyv * p.dy;
+          }
+          else if (k == p.jend - 1 && a.kp.edge_hi == EDGE_PHYSICAL)
+          {
+            fyh[0] = 0.0, fyh[1] = 0.0, fyh[3] = 0.0;
+            fyh[2] = fy_lo.pout + rho_k * gyv * p.dy;
+          }
+        }
+      }
+
+      double u4[4];
+      u4[0] = un[0] + (fxl.m - fxr.m) * dtdx + (fyl[0] - fyh[0]) * dtdy;
+      u4[1] = un[1] + (fxl.n - fxr.n) * dtdx + (fyl[1] - fyh[1]) * dtdy;
+      u4[2] = un[2] + (fxl.t - fxr.t) * dtdx + (fyl[2] - fyh[2]) * dtdy;
+      u4[3] = un[3] + (fxl.e - fxr.e) * dtdx + (fyl[3] - fyh[3]) * dtdy;
+      if constexpr (GRAV)
+      {
+        // Update.h:161-166: both sweeps add into IV (Q4)
+        u4[2] += dt * rho_k * gxv + dt * rho_k * gyv;
+        u4[3] += dt * 0.5 * (fxl.m + fxr.m) * gxv + dt * 0.5 * (fyl[0] + fyh[0]) * gyv;
+      }
+
+      if constexpr (DIFF)
+      {
+        const int sm = slot_of(k - 1), sc = slot_of(k), sp = slot_of(k + 1);
+        if (p.thermal_conductivity_active)
+        {
+          // ThermalConduction.h:47-106, T = P / rho
+          const double TC = S.ring[sc][3][t] * frcp(S.ring[sc][0][t]);
+          const double TL = S.ring[sc][3][tl] * frcp(S.ring[sc][0][tl]);
+          const double TR = S.ring[sc][3][tr] * frcp(S.ring[sc][0][tr]);
+          const double TU = S.ring[sm][3][t] * frcp(S.ring[sm][0][t]);
+          const double TD = S.ring[sp][3][t] * frcp(S.ring[sp][0][t]);
+          const double kap = p.kappa;
+          const double rdx = 1.0 / p.dx, rdy = 1.0 / p.dy;
+          double FL = kap * (TC - TL) * rdx;
+          double FR = kap * (TR - TC) * rdx;
+          double FU = kap * (TC - TU) * rdy;
+          double FD = kap * (TD - TC) * rdy;
+          if (k == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL && p.bctc_ymin != FV2D_BCTC_NONE)
+          {
+            if (p.bctc_ymin == FV2D_BCTC_FIXED_TEMPERATURE)
+              FL = kap * 2.0 * (TC - p.bctc_ymin_value) * rdy;
+            else if (p.bctc_ymin == FV2D_BCTC_FIXED_GRADIENT)
+              FL = kap * p.bctc_ymin_value;
+          }
+          if (k == p.jend - 1 && a.kp.edge_hi == EDGE_PHYSICAL && p.bctc_ymax != FV2D_BCTC_NONE)
+          {
+            if (p.bctc_ymax == FV2D_BCTC_FIXED_TEMPERATURE)
+              FR = kap * 2.0 * (p.bctc_ymax_value - TC) * rdy;
+            else if (p.bctc_ymax == FV2D_BCTC_FIXED_GRADIENT)
+              FR = kap * p.bctc_ymax_value;
+          }
+          u4[3] += dtdx * (FR - FL) + dtdy * (FD - FU);
+        }
+        if (p.viscosity_active)
+        {
+          // Viscosity.h:52-117 on the 3x3 (u,v) stencil; not divided by the cell size (Q8)
+          const double rdx = 1.0 / p.dx, rdy = 1.0 / p.dy, mu = p.mu;
+          const double c43 = 4.0 / 3.0, c23 = 2.0 / 3.0;
+          double su[3][3], sv[3][3];
+          const int rs[3] = {sm, sc, sp};
+          const int cs[3] = {tl, t, tr};
+#pragma unroll
+          for (int b = 0; b < 3; ++b)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+            {
+              su[b][c] = S.ring[rs[b]][1][cs[c]];
+              sv[b][c] = S.ring[rs[b]][2][cs[c]];
+            }
+          double fu = 0.0, fv = 0.0, fe = 0.0;
+#pragma unroll
+          for (int side = 1; side < 3; ++side)
+          {
+            const double sg = (side == 1 ? -mu : mu);
+            {
+              const double qiU = 0.5 * (su[1][side] + su[1][side - 1]);
+              const double qiV = 0.5 * (sv[1][side] + sv[1][side - 1]);
+              const double dudx = rdx * (su[1][side] - su[1][side - 1]);
+              const double dvdx = rdx * (sv[1][side] - sv[1][side - 1]);
+              const double dudy = 0.25 * rdy * (su[2][side] - su[0][side] + su[2][side - 1] - su[0][side - 1]);
+              const double dvdy = 0.25 * rdy * (sv[2][side] - sv[0][side] + sv[2][side - 1] - sv[0][side - 1]);
+              const double txx = c43 * dudx - c23 * dvdy;
+              const double txy = dvdx + dudy;
+              fu += sg * txx;
+              fv += sg * txy;
+              fe += sg * (txx * qiU + txy * qiV);
+            }
+            {
+              const double qiU = 0.5 * (su[side][1] + su[side - 1][1]);
+              const double qiV = 0.5 * (sv[side][1] + sv[side - 1][1]);
+              const double dudy = rdy * (su[side][1] - su[side - 1][1]);
+              const double dvdy = rdy * (sv[side][1] - sv[side - 1][1]);
+              const double dudx = 0.25 * rdx * (su[side][2] - su[side][0] + su[side - 1][2] - su[side - 1][0]);
+              const double dvdx = 0.25 * rdx * (sv[side][2] - sv[side][0] + sv[side - 1][2] - sv[side - 1][0]);
+              const double tyy = c43 * dvdy - c23 * dudx;
+              const double txy = dvdx + dudy;
+              fu += sg * txy;
+              fv += sg * tyy;
+              fe += sg * (txy * qiU + tyy * qiV);
+            }
+          }
+          u4[1] += dt * fu;
+          u4[2] += dt * fv;
+          u4[3] += dt * fe;
+        }
+      }
+
+      if (interior)
+      {
+        const long long o = ocol + (long long)k * L.pitch;
+        if (a.U0 != nullptr) // SSP-RK2 combine (Update.h:214-220)
+        {
+#pragma unroll
+          for (int f = 0; f < 4; ++f)
+            u4[f] = 0.5 * (a.U0[o + f * L.plane] + u4[f]);
+        }
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+          a.Uout[o + f * L.plane] = u4[f];
+
+        // consToPrim (States.h:32-43)
+        const double ir = frcp(u4[0]);
+        double qo[4];
+        qo[0] = u4[0];
+        qo[1] = u4[1] * ir;
+        qo[2] = u4[2] * ir;
+        qo[3] = (u4[3] - 0.5 * u4[0] * (qo[1] * qo[1] + qo[2] * qo[2])) * gm1;
+        if (a.final_stage)
+        {
+          // checkNegatives (SimInfo.h:612-633)
+          if (qo[0] < 0.0)
+          {
+            qo[0] = a.kp.eps_reset;
+            n_negr++;
+          }
+          if (qo[3] < 0.0)
+          {
+            qo[3] = a.kp.eps_reset;
+            n_negp++;
+          }
+          n_nan += (qo[0] != qo[0]) + (qo[1] != qo[1]) + (qo[2] != qo[2]) + (qo[3] != qo[3]);
+          // computeDt of the new state (ComputeDt.h:30-34)
+          const double cs = csound(gamma * qo[3], qo[0]);
+          const double h  = (cs + fabs(qo[1])) / p.dx + (cs + fabs(qo[2])) / p.dy;
+          inv_dt_max      = fmax(inv_dt_max, h);
+        }
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+          a.Qout[o + f * L.plane] = qo[f];
+      }
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+        un[f] = un_next[f];
+    }
+
+    // roll the column window
+    fy_lo = fy_hi;
+    yp    = yp1;
+    xm    = xm1;
+    rho_k = qn[0];
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+    {
+      qk[f] = qn[f];
+      qn[f] = qnn[f];
+    }
+  }
+
+  // ---- CTA reductions: CFL maximum and sanity counters
+  if (a.final_stage)
+  {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      inv_dt_max = fmax(inv_dt_max, __shfl_xor_sync(0xffffffffu, inv_dt_max, o));
+      n_negr += __shfl_xor_sync(0xffffffffu, n_negr, o);
+      n_negp += __shfl_xor_sync(0xffffffffu, n_negp, o);
+      n_nan += __shfl_xor_sync(0xffffffffu, n_nan, o);
+    }
+    __syncthreads(); // X2 is free now: reuse as scratch
+    double *red = &S.X2[0][0][0];
+    if ((t & 31) == 0)
+      red[t >> 5] = inv_dt_max;
+    __syncthreads();
+    if (t == 0)
+    {
+      double m = red[0];
+      for (int w = 1; w < NT / 32; ++w)
+        m = fmax(m, red[w]);
+      atomicMax(&a.kp.sc->inv_acc[a.acc_slot][0], encode_ordered(m));
+    }
+    if ((t & 31) == 0)
+    {
+      if (n_negr)
+        atomicAdd(&a.kp.sc->neg[0], (unsigned long long)n_negr);
+      if (n_negp)
+        atomicAdd(&a.kp.sc->neg[1], (unsigned long long)n_negp);
+      if (n_nan)
+        atomicAdd(&a.kp.sc->neg[2], (unsigned long long)n_nan);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------- step prologue
+
+__device__ __forceinline__ int bc_src(int bc, int k, int beg, int end, int N)
+{
+  switch (bc)
+  {
+  case FV2D_BC_REFLECTING:
+    return 2 * (k < beg ? beg : end) - k - 1;
+  case FV2D_BC_PERIODIC:
+    return k < beg ? k + N : k - N;
+  default:
+    return k < beg ? beg : end - 1;
+  }
+}
+
+// Ghost fill (BoundaryConditions.h:82-147; x and y passes composed, see fv2d_ops.cu) plus
+// the device-side clock: dt = CFL / max(inverse time-steps) (ComputeDt.h:64), t += dt
+// (main.cpp:83).
+__global__ void k_step_begin(KParams kp, double *__restrict__ Q, StepBeginArgs a)
+{
+  const fv2d_device_params &p = kp.p;
+  const long long tid         = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid == 0)
+  {
+    DevScalars *sc = kp.sc;
+    if (a.advance)
+    {
+      double dt;
+      if (a.use_device_dt)
+      {
+        const double hyp = decode_ordered(sc->inv_acc[a.acc_read][0]);
+        double tc = p.epsilon, visc = p.epsilon;
+        if (p.thermal_conductivity_active)
+          tc = fmax(2.0 * p.kappa / (p.dx * p.dx), 2.0 * p.kappa / (p.dy * p.dy));
+        if (p.viscosity_active)
+          visc = fmax(2.0 * p.mu / (p.dx * p.dx), 2.0 * p.mu / (p.dy * p.dy));
+        double m = hyp;
+        if (m < tc)
+          m = tc;
+        if (m < visc)
+          m = visc;
+        sc->inv_dt_last[0] = hyp;
+        sc->inv_dt_last[1] = tc;
+        sc->inv_dt_last[2] = visc;
+        dt                 = p.CFL / m;
+      }
+      else
+        dt = a.dt_host;
+      sc->dt                                    = dt;
+      sc->dt_hist[sc->step % FV2D_DT_HISTORY]   = dt;
+      sc->t += dt;
+      sc->step += 1;
+      sc->inv_acc[a.acc_reset][0] = FV2D_ENC_NEG_MAX;
+    }
+  }
+
+  const int Ng = p.Ng, Ntx = p.Ntx;
+  const long long n_y = 2LL * Ng * Ntx, n_x = 2LL * Ng * p.Ny;
+  if (tid >= n_y + n_x)
+    return;
+  int i, j;
+  if (tid < n_y)
+  {
+    const int r = int(tid / Ntx);
+    i           = int(tid - (long long)r * Ntx);
+    j           = (r < Ng) ? r : p.jend + (r - Ng);
+  }
+  else
+  {
+    const long long q = tid - n_y;
+    const int r       = int(q / (2 * Ng));
+    const int c       = int(q - (long long)r * (2 * Ng));
+    j                 = p.jbeg + r;
+    i                 = (c < Ng) ? c : p.iend + (c - Ng);
+  }
+  int js = j, is = i;
+  bool flip_u = false, flip_v = false;
+  if (j < p.jbeg || j >= p.jend)
+  {
+    if (((j < p.jbeg) ? kp.edge_lo : kp.edge_hi) != EDGE_PHYSICAL)
+      return;
+    js     = bc_src(p.boundary_y, j, p.jbeg, p.jend, p.Ny);
+    flip_v = (p.boundary_y == FV2D_BC_REFLECTING);
+  }
+  if (i < p.ibeg || i >= p.iend)
+  {
+    is     = bc_src(p.boundary_x, i, p.ibeg, p.iend, p.Nx);
+    flip_u = (p.boundary_x == FV2D_BC_REFLECTING);
+  }
+  const long long os = kp.L.at(0, is, js), od = kp.L.at(0, i, j);
+  const double r = Q[os], u = Q[os + kp.L.plane], v = Q[os + 2 * kp.L.plane], pr = Q[os + 3 * kp.L.plane];
+  Q[od]                   = r;
+  Q[od + kp.L.plane]      = flip_u ? -u : u;
+  Q[od + 2 * kp.L.plane]  = flip_v ? -v : v;
+  Q[od + 3 * kp.L.plane]  = pr;
+}
+
+void launch_step_begin(const KParams &kp, double *Q, const StepBeginArgs &a, cudaStream_t s)
+{
+  const long long n = 2LL * kp.p.Ng * kp.p.Ntx + 2LL * kp.p.Ng * kp.p.Ny;
+  k_step_begin<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(kp, Q, a);
+}
+
+// --------------------------------------------------------------------------- dispatch
+
+constexpr int kNT = 256;
+int sweep_strip_width() { return kNT - 4; }
+
+template <bool PLM, int SOLVER, bool GRAV, bool DIFF>
+static cudaError_t launch_one(const CUtensorMap &tm, const SweepArgs &a, cudaStream_t s, bool configure_only)
+{
+  auto kern             = k_sweep<kNT, PLM, SOLVER, GRAV, DIFF>;
+  constexpr size_t smem = sizeof(SweepSmem<kNT>);
+  if (configure_only)
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int W       = kNT - 4;
+  const int nstrips = (a.kp.p.Nx + W - 1) / W;
+  const int nchunks = (a.kp.p.Ny + a.chunk_rows - 1) / a.chunk_rows;
+  kern<<<dim3(nstrips, nchunks), kNT, smem, s>>>(tm, a);
+  return cudaGetLastError();
+}
+
+template <bool PLM, int SOLVER>
+static cudaError_t dispatch2(const CUtensorMap &tm, const SweepArgs &a, cudaStream_t s, bool cfg, bool grav, bool diff)
+{
+  if (grav)
+    return diff ? launch_one<PLM, SOLVER, true, true>(tm, a, s, cfg) : launch_one<PLM, SOLVER, true, false>(tm, a, s, cfg);
+  return diff ? launch_one<PLM, SOLVER, false, true>(tm, a, s, cfg) : launch_one<PLM, SOLVER, false, false>(tm, a, s, cfg);
+}
+
+template <bool PLM>
+static cudaError_t dispatch1(const CUtensorMap &tm, const SweepArgs &a, cudaStream_t s, bool cfg, int solver, bool grav,
+                             bool diff)
+{
+  switch (solver)
+  {
+  case FV2D_HLL:
+    return dispatch2<PLM, FV2D_HLL>(tm, a, s, cfg, grav, diff);
+  case FV2D_FSLP:
+    return dispatch2<PLM, FV2D_FSLP>(tm, a, s, cfg, grav, diff);
+  default:
+    return dispatch2<PLM, FV2D_HLLC>(tm, a, s, cfg, grav, diff);
+  }
+}
+
+cudaError_t launch_sweep(const CUtensorMap &tmapQ, const SweepArgs &a, cudaStream_t s)
+{
+  const fv2d_device_params &p = a.kp.p;
+  const bool plm  = (p.reconstruction == FV2D_PLM); // PCM_WB == PCM (Q3)
+  const bool grav = (p.gravity_mode != FV2D_GRAV_NONE);
+  const bool diff = p.thermal_conductivity_active || p.viscosity_active;
+  return plm ? dispatch1<true>(tmapQ, a, s, false, p.riemann_solver, grav, diff)
+             : dispatch1<false>(tmapQ, a, s, false, p.riemann_solver, grav, diff);
+}
+
+cudaError_t sweep_configure()
+{
+  CUtensorMap dummy;
+  memset(&dummy, 0, sizeof dummy);
+  SweepArgs a;
+  memset(&a, 0, sizeof a);
+  for (int plm = 0; plm < 2; ++plm)
+    for (int solver = 0; solver < 3; ++solver)
+      for (int grav = 0; grav < 2; ++grav)
+        for (int diff = 0; diff < 2; ++diff)
+        {
+          cudaError_t e = plm ? dispatch1<true>(dummy, a, nullptr, true, solver, grav, diff)
+                              : dispatch1<false>(dummy, a, nullptr, true, solver, grav, diff);
+          if (e != cudaSuccess)
+            return e;
+        }
+  return cudaSuccess;
+}
+
+} // namespace fv2d

@@ -1,0 +1,181 @@
+/* fv2d_b200.h — C ABI of libfv2d_b200.so: the B200-native (sm_100a) replacement for the
+ * per-timestep finite-volume update of mdelorme/fv2d.
+ *
+ * The reference has no FFI layer; its "operator surface" is a handful of C++ functor
+ * classes constructed from one Params object and driven by main.cpp.  Each entry point
+ * below names the reference interface it replaces (file:line in the reference tree).
+ * The C++ host mirror in fv2d_b200/host/ (UpdateFunctor, ComputeDtFunctor, ...) and the
+ * Python binding in fv2d_b200/capi.py are thin layers over exactly these symbols.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; fv2d_last_error() returns a
+ *     thread-local, human-readable description of the last failure;
+ *   - there is NO CPU fallback: on a machine without a usable sm_100 device every compute
+ *     entry point fails with FV2D_ERR_CUDA;
+ *   - host arrays are fp64 SoA planes over the full grid including ghosts,
+ *     A[f][j][i], f in 0..3 (rho,u,v,P | rho,rho*u,rho*v,E), j in 0..Nty-1, i in 0..Ntx-1,
+ *     no padding — i.e. the reference's Q(j,i,f) (main.cpp:33-34) with the field index
+ *     moved outermost;
+ *   - a context owns the device copies of Q and U (reference main.cpp:33-34), the scratch
+ *     arrays the reference functors own (slopes: Update.h:54-55; RK2 temporaries:
+ *     Update.h:200-201) and one CUDA stream.  Calls on one context are stream-ordered;
+ *     functions that return a value to the host synchronise that stream.
+ */
+#ifndef FV2D_B200_H_
+#define FV2D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "fv2d_params.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FV2D_OK 0
+#define FV2D_ERR_ARG 1         /* bad argument / unsupported configuration */
+#define FV2D_ERR_CUDA 2        /* CUDA runtime/driver failure, or no sm_100 device */
+#define FV2D_ERR_IO 3          /* file could not be read / written */
+#define FV2D_ERR_CONFIG 4      /* .ini error: duplicate key, bad enum string, unknown problem */
+
+typedef struct fv2d_ctx fv2d_ctx;
+
+const char *fv2d_last_error(void);
+/* ABI version of this header (bumped on incompatible change). */
+int fv2d_abi_version(void);
+
+/* ------------------------------------------------------------------ host-side setup */
+
+/* replaces readInifile(filename) -> Params                         (SimInfo.h:529-568)
+ * `overrides` is NULL or a ';'-separated list "section.key=value;..." applied as if the
+ * lines were present in the file.  Warnings about unknown sections/keys
+ * (checkValidityIni, SimInfo.h:501-527) go to stderr like the reference. */
+int fv2d_params_from_ini(const char *ini_path, const char *overrides, fv2d_device_params *dev, fv2d_run_params *run);
+
+/* replaces Reader::outputValues via IOManager's ctor                (SimInfo.h:224-262,
+ * IOManager.h:90-94): writes the effective configuration of `ini_path` to `out_path`. */
+int fv2d_params_dump_ini(const char *ini_path, const char *overrides, const char *out_path);
+
+/* replaces InitFunctor(params).init(Q)                              (Init.h:291-358)
+ * hostQ: zero-filled on entry by this function, then domain + ghosts are written. */
+int fv2d_init_problem(const fv2d_device_params *dev, const fv2d_run_params *run, double *hostQ);
+
+/* ------------------------------------------------------------------ context */
+
+/* Allocates Q and U (zero-filled, like Kokkos Views: main.cpp:33-34) on CUDA device
+ * `device`.  time_stepping = FV2D_TS_EULER / FV2D_TS_RK2 (Params::time_stepping,
+ * SimInfo.h:471); eps_reset_negative = Params::epsilon_reset_negative (SimInfo.h:491). */
+int fv2d_ctx_create(const fv2d_device_params *dev, int time_stepping, double eps_reset_negative, int device,
+                    fv2d_ctx **out);
+
+/* Multi-GPU variant: this process owns y-slab `rank` of `nranks` (rows
+ * [jbeg + rank*Ny/nranks, jbeg + (rank+1)*Ny/nranks) of the global grid described by `dev`;
+ * Ny must be divisible by nranks).  Ghost rows at slab interfaces are filled by
+ * fv2d_halo_* below instead of the physical y boundary condition. */
+int fv2d_ctx_create_slab(const fv2d_device_params *dev, int time_stepping, double eps_reset_negative, int device,
+                         int rank, int nranks, fv2d_ctx **out);
+void fv2d_ctx_destroy(fv2d_ctx *ctx);
+
+/* Optional: run all work of this context on an existing CUDA stream (cudaStream_t passed as
+ * void*), e.g. the caller's torch stream.  The context never destroys a borrowed stream. */
+int fv2d_ctx_set_stream(fv2d_ctx *ctx, void *cuda_stream);
+int fv2d_sync(fv2d_ctx *ctx);
+
+/* Geometry of the local slab: out[0..5] = {Ntx, Nty_local, Ny_local, j_global_offset, pitch, lead}. */
+int fv2d_ctx_geometry(const fv2d_ctx *ctx, int64_t out[6]);
+
+/* Host <-> device transfer of the (local) arrays, layout [f][Nty_local][Ntx].
+ * Replace Kokkos::deep_copy to/from a host mirror (IOManager.h:113-114, 196-197). */
+int fv2d_upload_Q(fv2d_ctx *ctx, const double *hostQ);
+int fv2d_upload_U(fv2d_ctx *ctx, const double *hostU);
+int fv2d_download_Q(fv2d_ctx *ctx, double *hostQ);
+int fv2d_download_U(fv2d_ctx *ctx, double *hostU);
+
+/* ------------------------------------------------------------------ operator-level API
+ * One entry point per reference operator, same semantics, same order of arithmetic
+ * (compiled without FMA contraction: results are bit-identical to the reference build). */
+
+/* primToCons(Q, U, params) over range_tot                           (SimInfo.h:589-600) */
+int fv2d_prim_to_cons(fv2d_ctx *ctx);
+/* consToPrim(U, Q, params) over range_tot                           (SimInfo.h:576-587) */
+int fv2d_cons_to_prim(fv2d_ctx *ctx);
+/* checkNegatives(Q, params); counts = {rho<0, P<0, NaN}             (SimInfo.h:602-646) */
+int fv2d_check_negatives(fv2d_ctx *ctx, uint64_t counts[3]);
+/* BoundaryManager::fillBoundaries(Q)                                (BoundaryConditions.h:82-147) */
+int fv2d_fill_boundaries(fv2d_ctx *ctx);
+/* ComputeDtFunctor::computeDt(Q, max_dt, t, diag); inv_dt = {hyp, tc, visc} (may be NULL)
+ *                                                                   (ComputeDt.h:18-65) */
+int fv2d_compute_dt(fv2d_ctx *ctx, double *dt, double inv_dt[3]);
+/* UpdateFunctor::computeSlopes(Q)                                   (Update.h:59-91) */
+int fv2d_compute_slopes(fv2d_ctx *ctx);
+/* UpdateFunctor::computeFluxesAndUpdate(Q, Unew, dt)                (Update.h:93-174) */
+int fv2d_compute_fluxes_and_update(fv2d_ctx *ctx, double dt);
+/* ThermalConductionFunctor::applyThermalConduction(Q, Unew, dt)     (ThermalConduction.h:36-108) */
+int fv2d_apply_thermal_conduction(fv2d_ctx *ctx, double dt);
+/* ViscosityFunctor::applyViscosity(Q, Unew, dt)                     (Viscosity.h:27-119) */
+int fv2d_apply_viscosity(fv2d_ctx *ctx, double dt);
+/* UpdateFunctor::euler_step(Q, Unew, dt)                            (Update.h:176-191) */
+int fv2d_euler_step(fv2d_ctx *ctx, double dt);
+/* UpdateFunctor::update(Q, Unew, dt): Euler or SSP-RK2, unfused     (Update.h:193-222) */
+int fv2d_update(fv2d_ctx *ctx, double dt);
+
+/* ------------------------------------------------------------------ fused hot path
+ * One time step of the reference loop body, main.cpp:66-83:
+ *     update.update(Q,U,dt); consToPrim(U,Q); checkNegatives(Q); [next computeDt]
+ * as one fused sm_100a kernel per Runge-Kutta stage (+ a ghost-fill kernel).  The kernel
+ * also reduces the inverse time-steps of the NEW state, so the next dt is already on the
+ * device when the step ends. */
+
+/* dt supplied by the host (the reference's calling convention). */
+int fv2d_step(fv2d_ctx *ctx, double dt);
+/* dt taken from the device-resident value (computed by the previous step, or by
+ * fv2d_compute_dt before the first one).  No host synchronisation. */
+int fv2d_step_device_dt(fv2d_ctx *ctx);
+/* nsteps x fv2d_step_device_dt, no host synchronisation (enqueues only). */
+int fv2d_run_steps(fv2d_ctx *ctx, int64_t nsteps);
+/* Replays main.cpp:62-84 without IO: steps while t + epsilon < tend, at most max_steps.
+ * Returns the number of steps done in *steps_done. */
+int fv2d_run_until(fv2d_ctx *ctx, double tend, int64_t max_steps, int64_t *steps_done);
+
+/* Device-resident clock: time, the dt the NEXT step would use, number of steps taken. */
+int fv2d_get_time(fv2d_ctx *ctx, double *t, double *next_dt, int64_t *steps);
+int fv2d_set_time(fv2d_ctx *ctx, double t);
+/* The dt used by each of the last min(n, steps, FV2D_DT_HISTORY) steps, oldest first;
+ * returns how many were written in *n_out. */
+#define FV2D_DT_HISTORY 4096
+int fv2d_get_dt_history(fv2d_ctx *ctx, double *dts, int64_t n, int64_t *n_out);
+/* Cumulative checkNegatives counters since context creation / last reset. */
+int fv2d_get_negative_counts(fv2d_ctx *ctx, uint64_t counts[3], int reset);
+/* Sum over the local domain of rho*dx*dy and E*dx*dy (the reference's only conservation
+ * diagnostic, python/plot_energy_evolution.py:28-47). */
+int fv2d_integrate_mass_energy(fv2d_ctx *ctx, double *mass, double *energy);
+
+/* Host-buffer convenience used for end-to-end measurement: upload Q (pinned or pageable
+ * host memory), primToCons, computeDt, run `nsteps` fused steps, download Q; dts (may be
+ * NULL) receives the dt sequence.  Equivalent to the reference main.cpp:58-84 on a state
+ * that lives on the host. */
+int fv2d_advance_host(fv2d_ctx *ctx, const double *hostQ_in, double *hostQ_out, int64_t nsteps, double *dts);
+
+/* ------------------------------------------------------------------ multi-GPU halo exchange
+ * (no reference counterpart: the reference is single-device.)  Rows are exchanged over
+ * peer memory (CUDA IPC): every rank publishes a handle to its Q buffers, opens its two
+ * y-neighbours' handles, and the stage epilogue's edge rows are written straight into the
+ * neighbour's ghost rows. */
+#define FV2D_IPC_HANDLE_BYTES 256
+/* Fills `handle` (FV2D_IPC_HANDLE_BYTES bytes) describing this rank's exchange buffers. */
+int fv2d_halo_export(fv2d_ctx *ctx, void *handle);
+/* handles: nranks consecutive handles gathered from all ranks (e.g. torch.distributed
+ * all_gather), index = rank. */
+int fv2d_halo_connect(fv2d_ctx *ctx, const void *handles, int nranks);
+/* Same-process variant (tests, single-process multi-GPU drivers). */
+int fv2d_halo_connect_local(fv2d_ctx **ctxs, int nranks);
+/* Global dt across ranks: each rank writes its three inverse-dt maxima into every peer's
+ * mailbox from the stage epilogue; the next step's prologue reduces them.  Nothing to call
+ * per step — these are here for diagnostics. */
+int fv2d_get_inv_dt(fv2d_ctx *ctx, double inv_dt[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FV2D_B200_H_ */
