@@ -24,10 +24,10 @@ $(OBJDIR)/fv2d_sweep.o: $(CSRC)/fv2d_sweep.cu $(HOSTHDR)
 
 $(OBJDIR)/fv2d_capi.o: $(CSRC)/fv2d_capi.cu $(HOSTHDR)
 	@mkdir -p $(OBJDIR)
-	$(NVCC) $(NVFLAGS) -c $< -o $@
+	$(NVCC) $(NVFLAGS) -Xcompiler -fopenmp -c $< -o $@
 
 $(LIB): $(OBJDIR)/fv2d_ops.o $(OBJDIR)/fv2d_sweep.o $(OBJDIR)/fv2d_capi.o
-	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static
+	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static -Xcompiler -fopenmp
 
 fv2d_b200/fv2d_b200_main: fv2d_b200/host/main.cpp $(HOSTHDR) $(LIB)
 	/usr/bin/g++ -std=c++17 -O2 -Wall -Iinclude fv2d_b200/host/main.cpp -o $@ -Lfv2d_b200 -lfv2d_b200 -Wl,-rpath,'$$ORIGIN'

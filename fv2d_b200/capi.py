@@ -179,6 +179,8 @@ def lib() -> C.CDLL:
         "fv2d_get_negative_counts": [_ctxp, C.POINTER(C.c_uint64), C.c_int],
         "fv2d_integrate_mass_energy": [_ctxp, _dp, _dp],
         "fv2d_advance_host": [_ctxp, _dp, _dp, C.c_int64, _dp],
+        "fv2d_profile_enable": [_ctxp, C.c_int],
+        "fv2d_profile_read": [_ctxp, _dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
         "fv2d_halo_export": [_ctxp, C.c_void_p],
         "fv2d_halo_connect": [_ctxp, C.c_void_p, C.c_int],
         "fv2d_halo_connect_local": [C.POINTER(_ctxp), C.c_int],
@@ -370,6 +372,14 @@ class Context:
         m, e = C.c_double(), C.c_double()
         _check(lib().fv2d_integrate_mass_energy(self._h, C.byref(m), C.byref(e)))
         return m.value, e.value
+
+    def profile_enable(self, on: bool = True):
+        _check(lib().fv2d_profile_enable(self._h, int(on)))
+
+    def profile_read(self):
+        ms, ns, nt = C.c_double(), C.c_int64(), C.c_int64()
+        _check(lib().fv2d_profile_read(self._h, C.byref(ms), C.byref(ns), C.byref(nt)))
+        return ms.value, ns.value, nt.value
 
     def advance_host(self, Q_in: np.ndarray, Q_out: np.ndarray, nsteps: int, dts: np.ndarray | None = None):
         _check(lib().fv2d_advance_host(self._h, _ptr(Q_in), _ptr(Q_out), nsteps, _ptr(dts) if dts is not None else None))

@@ -223,6 +223,18 @@ static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
   b.acc_reset     = c->acc_parity ^ 1;
   b.advance       = 1;
   launch_step_begin(c->kp, c->Q[cur], b, c->stream);
+  c->n_launch_total++;
+  auto prof_mark = [&](int which) {
+    if (c->profile && c->prof_n < kProfMax)
+      cudaEventRecord(c->prof_ev[2 * c->prof_n + which], c->stream);
+    if (which == 1)
+    {
+      c->n_launch_sweep++;
+      c->n_launch_total++;
+      if (c->profile && c->prof_n < kProfMax)
+        c->prof_n++;
+    }
+  };
 
   SweepArgs a;
   a.kp         = c->kp;
@@ -237,15 +249,20 @@ static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
       return rc;
     // stage 1: U* = U + dt L(Q), Q* = consToPrim(U*)           (Update.h:204-210)
     a.Uin = c->U, a.Uout = c->Ustar, a.U0 = nullptr, a.Qout = c->Q[nxt], a.final_stage = 0;
+    prof_mark(0);
     e = launch_sweep(c->tmapQ[cur], a, c->stream);
+    prof_mark(1);
     if (e != cudaSuccess)
       return cuda_fail(e, "sweep stage 1", __FILE__, __LINE__);
     // ghosts of Q*, no clock advance                              (Update.h:211 -> :179)
     b.advance = 0;
     launch_step_begin(c->kp, c->Q[nxt], b, c->stream);
+    c->n_launch_total++;
     // stage 2: U = 0.5 (U0 + U* + dt L(Q*)), Q = consToPrim(U)    (Update.h:211-220, main.cpp:80-81)
     a.Uin = c->Ustar, a.Uout = c->U, a.U0 = c->U, a.Qout = c->Q[cur], a.final_stage = 1;
+    prof_mark(0);
     e = launch_sweep(c->tmapQ[nxt], a, c->stream);
+    prof_mark(1);
     if (e != cudaSuccess)
       return cuda_fail(e, "sweep stage 2", __FILE__, __LINE__);
     // Q[cur] holds the new state again
@@ -253,7 +270,9 @@ static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
   else
   {
     a.Uin = c->U, a.Uout = c->U, a.U0 = nullptr, a.Qout = c->Q[nxt], a.final_stage = 1;
+    prof_mark(0);
     e = launch_sweep(c->tmapQ[cur], a, c->stream);
+    prof_mark(1);
     if (e != cudaSuccess)
       return cuda_fail(e, "sweep", __FILE__, __LINE__);
     c->cur = nxt;
@@ -269,6 +288,7 @@ static int compute_dt_now(fv2d_ctx *c)
   FV2D_CUDA(cudaMemcpyAsync(&c->sc->inv_acc[c->acc_parity][0], &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
   launch_compute_dt(c->kp, c->Q[c->cur], &c->sc->inv_acc[c->acc_parity][0], c->stream);
   launch_finalize_dt(c->kp, &c->sc->inv_acc[c->acc_parity][0], c->stream);
+  c->n_launch_total += 2;
   FV2D_CUDA(cudaGetLastError());
   return FV2D_OK;
 }
@@ -504,6 +524,12 @@ void fv2d_ctx_destroy(fv2d_ctx *c)
   cudaFree(c->slopesY);
   cudaFree(c->gtab);
   cudaFree(c->sc);
+  if (c->prof_ev)
+  {
+    for (int k = 0; k < 2 * kProfMax; ++k)
+      cudaEventDestroy(c->prof_ev[k]);
+    delete[] c->prof_ev;
+  }
   if (c->sc_host)
     cudaFreeHost(c->sc_host);
   if (c->stage_host)
@@ -843,6 +869,43 @@ int fv2d_integrate_mass_energy(fv2d_ctx *c, double *mass, double *energy)
   return FV2D_OK;
 }
 
+int fv2d_profile_enable(fv2d_ctx *c, int on)
+{
+  FV2D_ENTER(c);
+  if (on && !c->prof_ev)
+  {
+    c->prof_ev = new cudaEvent_t[2 * kProfMax];
+    for (int k = 0; k < 2 * kProfMax; ++k)
+      FV2D_CUDA(cudaEventCreate(&c->prof_ev[k]));
+  }
+  c->profile        = on != 0;
+  c->prof_n         = 0;
+  c->n_launch_sweep = 0;
+  c->n_launch_total = 0;
+  return FV2D_OK;
+}
+int fv2d_profile_read(fv2d_ctx *c, double *sweep_ms, int64_t *sweep_launches, int64_t *total_launches)
+{
+  FV2D_ENTER(c);
+  int rc;
+  if ((rc = sync_ctx(c)))
+    return rc;
+  double ms = 0.0;
+  for (int k = 0; k < c->prof_n; ++k)
+  {
+    float x = 0.f;
+    FV2D_CUDA(cudaEventElapsedTime(&x, c->prof_ev[2 * k], c->prof_ev[2 * k + 1]));
+    ms += x;
+  }
+  if (sweep_ms)
+    *sweep_ms = ms;
+  if (sweep_launches)
+    *sweep_launches = c->prof_n;
+  if (total_launches)
+    *total_launches = c->n_launch_total;
+  return FV2D_OK;
+}
+
 int fv2d_advance_host(fv2d_ctx *c, const double *hostQ_in, double *hostQ_out, int64_t nsteps, double *dts)
 {
   FV2D_ENTER(c);
@@ -852,6 +915,7 @@ int fv2d_advance_host(fv2d_ctx *c, const double *hostQ_in, double *hostQ_out, in
   if ((rc = copy_h2d(c, c->Q[c->cur], hostQ_in)))
     return rc;
   launch_prim_to_cons(c->kp, c->Q[c->cur], c->U, c->stream);
+  c->n_launch_total++;
   if ((rc = compute_dt_now(c)))
     return rc;
   for (int64_t k = 0; k < nsteps; ++k)

@@ -91,6 +91,7 @@ __host__ __device__ inline double decode_ordered(unsigned long long e)
 }
 // encode_ordered(-DBL_MAX): identity of the Max reducers (Kokkos::Max, ComputeDt.h:50-52)
 #define FV2D_ENC_NEG_MAX 0x0010000000000000ULL
+constexpr int kProfMax = 8192;
 
 void set_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
@@ -130,6 +131,12 @@ struct fv2d_ctx
   CUtensorMap tmapQ[2]; // TMA descriptors of Q[0], Q[1]
   bool tmap_ok;
   int acc_parity; // which inv_acc slot the NEXT sweep accumulates into
+
+  // optional profiling: CUDA event pairs around every sweep launch
+  bool profile;
+  cudaEvent_t *prof_ev; // 2 * kProfMax events
+  int prof_n;           // pairs recorded
+  long long n_launch_sweep, n_launch_total;
 
   // multi-GPU peers (slab above / below)
   double *peerQ_lo[2], *peerQ_hi[2]; // neighbour's Q[0], Q[1] (mapped through IPC / peer access)

@@ -68,6 +68,22 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, 
                : "memory");
 }
 
+// Predicated fp64 global load issued HERE (asm volatile keeps it above the row barrier), so
+// the HBM latency overlaps the whole row of arithmetic instead of stalling the first use.
+__device__ __forceinline__ double ldg_stream(const double *ptr, int pred)
+{
+  double v;
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "setp.ne.b32 p, %2, 0;\n"
+               "mov.f64 %0, 0d0000000000000000;\n"
+               "@p ld.global.L1::no_allocate.f64 %0, [%1];\n"
+               "}\n"
+               : "=d"(v)
+               : "l"(ptr), "r"(pred));
+  return v;
+}
+
 // 1/a: MUFU.RCP64H seed (>= 20 bits) + two Newton steps -> ~1 ulp, no slow path
 __device__ __forceinline__ double frcp(double a)
 {
@@ -255,6 +271,8 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
   const int tl = (t > 0 ? t - 1 : 0), tr = (t < NT - 1 ? t + 1 : NT - 1);
 
   const double dt    = a.kp.sc->dt;
+  const double rdx   = 1.0 / p.dx;
+  const double rdy   = 1.0 / p.dy;
   const double dtdx  = dt / p.dx;
   const double dtdy  = dt / p.dy;
   const double gamma = p.gamma0;
@@ -321,23 +339,27 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
   fy_lo.m = fy_lo.n = fy_lo.t = fy_lo.e = fy_lo.pout = 0.0;
   xm.r = xm.n = xm.t = xm.p = xm.c = 0.0;
 
-  // U prefetch (row j0), own column, straight from global memory (coalesced, read once)
-  double un[4] = {0.0, 0.0, 0.0, 0.0};
   const long long ocol = L.at(0, col, 0);
-  if (interior)
-  {
-#pragma unroll
-    for (int f = 0; f < 4; ++f)
-      un[f] = a.Uin[ocol + f * L.plane + (long long)j0 * L.pitch];
-  }
+  const double *Ucol   = a.Uin + ocol;
 
   double inv_dt_max = -1.7976931348623157e308;
   unsigned n_negr = 0, n_negp = 0, n_nan = 0;
 
   // ---- march: iteration k finishes row k; k = j0-1 is the warm-up (no update)
+#pragma unroll 2
   for (int k = j0 - 1; k < j1; ++k)
   {
     const int par = k & 1;
+    // U of row k, own column, straight from global memory (coalesced, read once); issued at
+    // the top of the row so its latency hides behind the row's arithmetic
+    double un[4];
+    {
+      const int pred      = interior && (k >= j0);
+      const double *urow  = Ucol + (long long)k * L.pitch;
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+        un[f] = ldg_stream(urow + f * L.plane, pred);
+    }
     // A. new row k+2 enters; y slopes / face states of row k+1; y-face flux at k+1/2
     wait_row(k + 2);
     double qnn[4];
@@ -377,7 +399,8 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
     FaceFlux fy_hi = riemann_f<SOLVER>(yp, ym, entho, gdy, p.fslp_K);
 
     // B. x-face flux at the left face of (col, k): left state from the neighbour thread
-    if (k >= j0)
+    //    (also runs, on don't-care data, in the warm-up iteration: no branch, so the x and y
+    //    Riemann problems of a row can be scheduled together)
     {
       FaceState xl;
       xl.r = S.X1[par][0][tl];
@@ -444,17 +467,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
     }
 
     // D. finish row k
-    if (k >= j0)
     {
-      // next row's U: issue the loads now, consume them next iteration
-      double un_next[4] = {0.0, 0.0, 0.0, 0.0};
-      if (interior && k + 1 < j1)
-      {
-#pragma unroll
-        for (int f = 0; f < 4; ++f)
-          un_next[f] = a.Uin[ocol + f * L.plane + (long long)(k + 1) * L.pitch];
-      }
-
       FaceFlux fxr;
       fxr.m = S.X2[par][0][tr];
       fxr.n = S.X2[par][1][tr];
@@ -515,7 +528,6 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
           const double TU = S.ring[sm][3][t] * frcp(S.ring[sm][0][t]);
           const double TD = S.ring[sp][3][t] * frcp(S.ring[sp][0][t]);
           const double kap = p.kappa;
-          const double rdx = 1.0 / p.dx, rdy = 1.0 / p.dy;
           double FL = kap * (TC - TL) * rdx;
           double FR = kap * (TR - TC) * rdx;
           double FU = kap * (TC - TU) * rdy;
@@ -539,7 +551,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
         if (p.viscosity_active)
         {
           // Viscosity.h:52-117 on the 3x3 (u,v) stencil; not divided by the cell size (Q8)
-          const double rdx = 1.0 / p.dx, rdy = 1.0 / p.dy, mu = p.mu;
+          const double mu = p.mu;
           const double c43 = 4.0 / 3.0, c23 = 2.0 / 3.0;
           double su[3][3], sv[3][3];
           const int rs[3] = {sm, sc, sp};
@@ -590,7 +602,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
         }
       }
 
-      if (interior)
+      if (interior && k >= j0)
       {
         const long long o = ocol + (long long)k * L.pitch;
         if (a.U0 != nullptr) // SSP-RK2 combine (Update.h:214-220)
@@ -626,16 +638,13 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
           n_nan += (qo[0] != qo[0]) + (qo[1] != qo[1]) + (qo[2] != qo[2]) + (qo[3] != qo[3]);
           // computeDt of the new state (ComputeDt.h:30-34)
           const double cs = csound(gamma * qo[3], qo[0]);
-          const double h  = (cs + fabs(qo[1])) / p.dx + (cs + fabs(qo[2])) / p.dy;
+          const double h  = (cs + fabs(qo[1])) * rdx + (cs + fabs(qo[2])) * rdy;
           inv_dt_max      = fmax(inv_dt_max, h);
         }
 #pragma unroll
         for (int f = 0; f < 4; ++f)
           a.Qout[o + f * L.plane] = qo[f];
       }
-#pragma unroll
-      for (int f = 0; f < 4; ++f)
-        un[f] = un_next[f];
     }
 
     // roll the column window

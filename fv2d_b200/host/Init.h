@@ -134,10 +134,25 @@ public:
     XorShift64Pool1 pool{uint64_t(full_params.seed)};
 
     // The reference's one-thread host iteration order is i outer, j inner
-    // (KokkosExp_MDRangePolicy.hpp:138-146, 328-345); it only matters for the RNG draws.
-    for (int i = p.ibeg; i < p.iend; ++i)
-      for (int j = p.jbeg; j < p.jend; ++j)
+    // (KokkosExp_MDRangePolicy.hpp:138-146, 328-345); it only matters for the RNG draws of
+    // H84 / C91, which therefore run in that order on one thread.  The other problems are
+    // pure functions of (i, j) and are filled row-parallel.
+    const bool sequential = (init_type == H84 || init_type == C91);
+    const long long ncell = (long long)p.Nx * p.Ny;
+#pragma omp parallel for schedule(static) if (!sequential)
+    for (long long cell = 0; cell < ncell; ++cell)
       {
+        int i, j;
+        if (sequential)
+        {
+          i = p.ibeg + int(cell / p.Ny);
+          j = p.jbeg + int(cell % p.Ny);
+        }
+        else
+        {
+          j = p.jbeg + int(cell / p.Nx);
+          i = p.ibeg + int(cell % p.Nx);
+        }
         real_t pos[2];
         getPos(p, i, j, pos);
         const real_t x = pos[IX], y = pos[IY];

@@ -151,6 +151,13 @@ int fv2d_get_negative_counts(fv2d_ctx *ctx, uint64_t counts[3], int reset);
  * diagnostic, python/plot_energy_evolution.py:28-47). */
 int fv2d_integrate_mass_energy(fv2d_ctx *ctx, double *mass, double *energy);
 
+/* Measurement hooks (bench.py): when enabled, every sweep launch is bracketed by a pair of
+ * CUDA events on the context's stream; fv2d_profile_read synchronises and returns the summed
+ * sweep time, the number of sweep launches and the number of all kernel launches since
+ * fv2d_profile_enable(ctx, 1). */
+int fv2d_profile_enable(fv2d_ctx *ctx, int on);
+int fv2d_profile_read(fv2d_ctx *ctx, double *sweep_ms, int64_t *sweep_launches, int64_t *total_launches);
+
 /* Host-buffer convenience used for end-to-end measurement: upload Q (pinned or pageable
  * host memory), primToCons, computeDt, run `nsteps` fused steps, download Q; dts (may be
  * NULL) receives the dt sequence.  Equivalent to the reference main.cpp:58-84 on a state
