@@ -30,7 +30,7 @@ $(LIB): $(OBJDIR)/fv2d_ops.o $(OBJDIR)/fv2d_sweep.o $(OBJDIR)/fv2d_capi.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static -Xcompiler -fopenmp
 
 fv2d_b200/fv2d_b200_main: fv2d_b200/host/main.cpp $(HOSTHDR) $(LIB)
-	/usr/bin/g++ -std=c++17 -O2 -Wall -Iinclude fv2d_b200/host/main.cpp -o $@ -Lfv2d_b200 -lfv2d_b200 -Wl,-rpath,'$$ORIGIN'
+	/usr/bin/g++ -std=c++17 -O2 -Wall -fopenmp -Iinclude fv2d_b200/host/main.cpp -o $@ -Lfv2d_b200 -lfv2d_b200 -Wl,-rpath,'$$ORIGIN'
 
 oracle:
 	$(MAKE) -C oracle oracle

@@ -391,4 +391,4 @@ def exported_symbols_in_header() -> list[str]:
 
     text = (_HERE.parent / "include" / "fv2d_b200.h").read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(fv2d_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(fv2d_[A-Za-z0-9_]+)\s*\(", text)))

@@ -845,11 +845,20 @@ int fv2d_get_negative_counts(fv2d_ctx *c, uint64_t counts[3], int reset)
 int fv2d_get_inv_dt(fv2d_ctx *c, double inv_dt[3])
 {
   FV2D_ENTER(c);
+  if (!inv_dt)
+    return arg_fail("null output");
   int rc;
   if ((rc = read_scalars(c)))
     return rc;
-  for (int k = 0; k < 3; ++k)
-    inv_dt[k] = c->sc_host->inv_dt_last[k];
+  // maxima of the CURRENT state (what the next step's dt is made of), ComputeDt.h:30-52
+  const fv2d_device_params &p = c->kp.p;
+  inv_dt[0] = decode_ordered(c->sc_host->inv_acc[c->acc_parity][0]);
+  inv_dt[1] = p.epsilon;
+  inv_dt[2] = p.epsilon;
+  if (p.thermal_conductivity_active)
+    inv_dt[1] = std::fmax(2.0 * p.kappa / (p.dx * p.dx), 2.0 * p.kappa / (p.dy * p.dy));
+  if (p.viscosity_active)
+    inv_dt[2] = std::fmax(2.0 * p.mu / (p.dx * p.dx), 2.0 * p.mu / (p.dy * p.dy));
   return FV2D_OK;
 }
 int fv2d_integrate_mass_energy(fv2d_ctx *c, double *mass, double *energy)

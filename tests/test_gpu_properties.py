@@ -1,0 +1,113 @@
+"""Size-independent properties of the CUDA path at sizes the oracle cannot reach in seconds
+(conservation with periodic BCs, uniform-state preservation, x/y symmetry,
+independence of the work decomposition, fused vs operator-level agreement)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_l1
+from fv2d_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(dev, run, Q0, nsteps, fused=True, chunk_rows=None):
+    old = os.environ.get("FV2D_CHUNK_ROWS")
+    if chunk_rows:
+        os.environ["FV2D_CHUNK_ROWS"] = str(chunk_rows)
+    try:
+        with capi.Context(dev, run.time_stepping, run.epsilon_reset_negative) as ctx:
+            ctx.upload_Q(Q0)
+            ctx.prim_to_cons()
+            dt0, _ = ctx.compute_dt()
+            m0 = ctx.mass_energy()
+            if fused:
+                ctx.run_steps(nsteps)
+                dts = ctx.dt_history(nsteps)
+            else:
+                dts = []
+                for _ in range(nsteps):
+                    dt, _ = ctx.compute_dt()
+                    dts.append(dt)
+                    ctx.update(dt)
+                    ctx.cons_to_prim()
+                    ctx.check_negatives()
+                dts = np.array(dts)
+            return ctx.download_Q(), ctx.download_U(), dts, m0, ctx.mass_energy(), ctx.negative_counts()
+    finally:
+        if chunk_rows:
+            if old is None:
+                os.environ.pop("FV2D_CHUNK_ROWS", None)
+            else:
+                os.environ["FV2D_CHUNK_ROWS"] = old
+
+
+def test_periodic_blast_2048_conserves_mass_and_energy():
+    dev, run = capi.params_from_ini(load_golden("blast_64").ini_path(), {"mesh.Nx": 2048, "mesh.Ny": 2048})
+    Q0 = capi.init_problem(dev, run)
+    Q, U, dts, m0, m1, neg = _run(dev, run, Q0, 20)
+    assert neg == [0, 0, 0] and np.all(np.isfinite(U))
+    assert abs(m1[0] - m0[0]) <= 1e-12 * abs(m0[0])
+    assert abs(m1[1] - m0[1]) <= 1e-12 * abs(m0[1])
+    # 4-fold symmetry of the centred blast survives (x <-> y transposition with u <-> v)
+    d = U[:, dev.jbeg:dev.jend, dev.ibeg:dev.iend]
+    assert rel_l1(d[0], d[0].T) <= 1e-12 and rel_l1(d[1], d[2].T) <= 1e-12
+
+
+@pytest.mark.parametrize("recon", ["pcm", "plm"])
+def test_uniform_state_is_preserved_at_full_width(recon):
+    dev, run = capi.params_from_ini(load_golden("kh_plm_128x64").ini_path(),
+                                    {"mesh.Nx": 1000, "mesh.Ny": 300, "solvers.reconstruction": recon})
+    Q0 = np.zeros(dev.shape())
+    Q0[0], Q0[1], Q0[2], Q0[3] = 1.3, 0.4, -0.2, 2.0
+    Q, U, dts, m0, m1, neg = _run(dev, run, Q0, 8)
+    d = Q[:, dev.jbeg:dev.jend, dev.ibeg:dev.iend]
+    for f, v in enumerate((1.3, 0.4, -0.2, 2.0)):
+        assert np.max(np.abs(d[f] - v)) <= 1e-13 * abs(v)
+
+
+def test_result_is_independent_of_the_work_decomposition():
+    """Strips / chunks only change who computes a face flux, never its value."""
+    dev, run = capi.params_from_ini(load_golden("kh_plm_128x64").ini_path(), {"mesh.Nx": 777, "mesh.Ny": 333})
+    Q0 = capi.init_problem(dev, run)
+    ref = _run(dev, run, Q0, 6, chunk_rows=64)
+    for cr in (1, 7, 50, 333, 1000):
+        got = _run(dev, run, Q0, 6, chunk_rows=cr)
+        assert np.array_equal(got[1], ref[1]), cr
+        assert np.array_equal(got[2], ref[2]), cr
+
+
+@pytest.mark.parametrize("name,ov", [
+    ("kh_plm_128x64", {"mesh.Nx": 1024, "mesh.Ny": 512}),
+    ("rt_plm_32x96", {"mesh.Nx": 520, "mesh.Ny": 700}),
+    ("c91_64x32", {"mesh.Nx": 600, "mesh.Ny": 300}),
+    ("gresho_rk2_32", {"mesh.Nx": 515, "mesh.Ny": 509}),
+    ("kh_plm_hll_64x32", {"mesh.Nx": 640, "mesh.Ny": 200}),
+    ("rt_fslp_32x96", {"mesh.Nx": 300, "mesh.Ny": 500}),
+])
+def test_fused_agrees_with_bit_exact_operator_path_at_scale(name, ov):
+    """The operator-level path is bit-identical to the reference (test_gpu_parity); at sizes
+    spanning several strips and chunks the fused kernel must stay within the parity bar of it."""
+    dev, run = capi.params_from_ini(load_golden(name).ini_path(), ov)
+    Q0 = capi.init_problem(dev, run)
+    a = _run(dev, run, Q0, 10, fused=True)
+    b = _run(dev, run, Q0, 10, fused=False)
+    assert np.max(np.abs(a[2] - b[2]) / b[2]) <= 1e-13
+    da = a[1][:, dev.jbeg:dev.jend, dev.ibeg:dev.iend]
+    db = b[1][:, dev.jbeg:dev.jend, dev.ibeg:dev.iend]
+    assert rel_l1(da, db) <= 1e-12
+    assert rel_l1(da[0], db[0]) <= 1e-12 and rel_l1(da[3], db[3]) <= 1e-12
+
+
+def test_sod_x_y_symmetry_on_device():
+    gx, gy = load_golden("sod_x"), load_golden("sod_y")
+    res = []
+    for g in (gx, gy):
+        dev, run = capi.params_from_ini(g.ini_path(), {"mesh.Nx": 512 if g is gx else 64, "mesh.Ny": 64 if g is gx else 512})
+        Q0 = capi.init_problem(dev, run)
+        Q, U, dts, *_ = _run(dev, run, Q0, 10)
+        res.append((Q[:, dev.jbeg:dev.jend, dev.ibeg:dev.iend], dts))
+    assert np.max(np.abs(res[0][1] - res[1][1]) / res[0][1]) <= 1e-13
+    assert rel_l1(res[0][0][0], res[1][0][0].T) <= 1e-12
+    assert rel_l1(res[0][0][3], res[1][0][3].T) <= 1e-12
