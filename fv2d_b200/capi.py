@@ -17,7 +17,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libfv2d_b200.so"
 
 FV2D_DT_HISTORY = 4096
-FV2D_IPC_HANDLE_BYTES = 256
+FV2D_IPC_HANDLE_BYTES = 512
 
 # enums of include/fv2d_params.h
 HLL, HLLC, FSLP = 0, 1, 2
@@ -182,8 +182,7 @@ def lib() -> C.CDLL:
         "fv2d_profile_enable": [_ctxp, C.c_int],
         "fv2d_profile_read": [_ctxp, _dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
         "fv2d_halo_export": [_ctxp, C.c_void_p],
-        "fv2d_halo_connect": [_ctxp, C.c_void_p, C.c_int],
-        "fv2d_halo_connect_local": [C.POINTER(_ctxp), C.c_int],
+        "fv2d_halo_connect": [_ctxp, C.c_char_p, C.c_int],
         "fv2d_get_inv_dt": [_ctxp, _dp],
     }
     for name, argtypes in sig.items():
@@ -372,6 +371,20 @@ class Context:
         m, e = C.c_double(), C.c_double()
         _check(lib().fv2d_integrate_mass_energy(self._h, C.byref(m), C.byref(e)))
         return m.value, e.value
+
+    def halo_export(self) -> bytes:
+        buf = C.create_string_buffer(FV2D_IPC_HANDLE_BYTES)
+        _check(lib().fv2d_halo_export(self._h, buf))
+        return buf.raw
+
+    def halo_connect(self, handles: bytes, nranks: int):
+        assert len(handles) == nranks * FV2D_IPC_HANDLE_BYTES
+        _check(lib().fv2d_halo_connect(self._h, handles, nranks))
+
+    def inv_dt(self):
+        inv = (C.c_double * 3)()
+        _check(lib().fv2d_get_inv_dt(self._h, inv))
+        return [float(v) for v in inv]
 
     def profile_enable(self, on: bool = True):
         _check(lib().fv2d_profile_enable(self._h, int(on)))

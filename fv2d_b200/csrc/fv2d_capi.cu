@@ -7,6 +7,8 @@
 #include <sstream>
 #include <vector>
 
+#include <unistd.h>
+
 #include "../host/Init.h"
 #include "../host/SimInfo.h"
 #include "fv2d_kernels.h"
@@ -154,7 +156,24 @@ static int sync_ctx(fv2d_ctx *c)
 static int read_scalars(fv2d_ctx *c)
 {
   FV2D_CUDA(cudaMemcpyAsync(c->sc_host, c->sc, offsetof(DevScalars, dt_hist), cudaMemcpyDeviceToHost, c->stream));
-  return sync_ctx(c);
+  int rc = sync_ctx(c);
+  if (rc)
+    return rc;
+  if (c->sc_host->fault)
+  {
+    set_error("a wait on a peer GPU timed out (halo rows or CFL mail never arrived)");
+    return FV2D_ERR_CUDA;
+  }
+  return FV2D_OK;
+}
+
+// the hyperbolic maximum of the CURRENT state, reduced over all slabs (latest mail generation)
+static double current_hyp(const fv2d_ctx *c)
+{
+  double m = -1.7976931348623157e308;
+  for (int q = 0; q < c->nranks; ++q)
+    m = std::fmax(m, c->sc_host->mail_inv[c->mail_gen & 1][q]);
+  return m;
 }
 
 // ------------------------------------------------------------------ step drivers
@@ -206,7 +225,26 @@ static int choose_chunk_rows(const fv2d_ctx *c)
   const char *env = std::getenv("FV2D_CHUNK_ROWS");
   if (env && std::atoi(env) > 0)
     return std::atoi(env);
-  return c->kp.p.Ny < 64 ? c->kp.p.Ny : 64;
+  // Work items (strip x chunk CTAs) all cost the same, so the sweep runs in waves of
+  // (#SMs x 2 resident CTAs): pick the chunk height that best fills the last wave, weighed
+  // against the ~1.5-row warm-up every chunk pays.
+  const int Ny = c->kp.p.Ny, W = sweep_strip_width();
+  const int nstrips = (c->kp.p.Nx + W - 1) / W;
+  const int slots   = 2 * c->num_sms;
+  int best = Ny < 64 ? Ny : 64;
+  double best_eff = -1.0;
+  for (int cr = 16; cr <= 96 && cr <= Ny; ++cr)
+  {
+    const long long ncta = (long long)nstrips * ((Ny + cr - 1) / cr);
+    const long long waves = (ncta + slots - 1) / slots;
+    const double eff = (double)ncta / (double)(waves * slots) * (cr / (cr + 1.5));
+    if (eff > best_eff)
+    {
+      best_eff = eff;
+      best     = cr;
+    }
+  }
+  return best;
 }
 
 // One fused time step (Euler: 1 sweep; RK2: 2 sweeps), dt either from the host or from the
@@ -222,6 +260,11 @@ static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
   b.acc_read      = c->acc_parity;
   b.acc_reset     = c->acc_parity ^ 1;
   b.advance       = 1;
+  if (c->nranks > 1 && !c->connected)
+    return arg_fail("multi-GPU context: call fv2d_halo_connect before stepping");
+  const unsigned long long pushes_per_sweep = 2ULL * ((c->kp.p.Nx + sweep_strip_width() - 1) / sweep_strip_width());
+  b.mail_gen      = c->mail_gen;
+  b.halo_expected = c->halo_gen * pushes_per_sweep;
   launch_step_begin(c->kp, c->Q[cur], b, c->stream);
   c->n_launch_total++;
   auto prof_mark = [&](int which) {
@@ -241,6 +284,13 @@ static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
   a.chunk_rows = choose_chunk_rows(c);
   a.n_strips   = 0;
   a.acc_slot   = c->acc_parity ^ 1;
+  a.lo_rank    = (c->rank + c->nranks - 1) % c->nranks;
+  a.hi_rank    = (c->rank + 1) % c->nranks;
+  a.mail_gen   = c->mail_gen + 1; // the final stage of this step posts the next generation
+  auto set_peers = [&](int qout) {
+    a.peer_lo_Qout = (c->kp.edge_lo == EDGE_NEIGHBOUR) ? c->peerQ_lo[qout] : nullptr;
+    a.peer_hi_Qout = (c->kp.edge_hi == EDGE_NEIGHBOUR) ? c->peerQ_hi[qout] : nullptr;
+  };
   cudaError_t e;
   if (c->time_stepping == FV2D_TS_RK2)
   {
@@ -249,17 +299,21 @@ static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
       return rc;
     // stage 1: U* = U + dt L(Q), Q* = consToPrim(U*)           (Update.h:204-210)
     a.Uin = c->U, a.Uout = c->Ustar, a.U0 = nullptr, a.Qout = c->Q[nxt], a.final_stage = 0;
+    set_peers(nxt);
     prof_mark(0);
     e = launch_sweep(c->tmapQ[cur], a, c->stream);
     prof_mark(1);
     if (e != cudaSuccess)
       return cuda_fail(e, "sweep stage 1", __FILE__, __LINE__);
+    c->halo_gen++;
     // ghosts of Q*, no clock advance                              (Update.h:211 -> :179)
-    b.advance = 0;
+    b.advance       = 0;
+    b.halo_expected = c->halo_gen * pushes_per_sweep;
     launch_step_begin(c->kp, c->Q[nxt], b, c->stream);
     c->n_launch_total++;
     // stage 2: U = 0.5 (U0 + U* + dt L(Q*)), Q = consToPrim(U)    (Update.h:211-220, main.cpp:80-81)
     a.Uin = c->Ustar, a.Uout = c->U, a.U0 = c->U, a.Qout = c->Q[cur], a.final_stage = 1;
+    set_peers(cur);
     prof_mark(0);
     e = launch_sweep(c->tmapQ[nxt], a, c->stream);
     prof_mark(1);
@@ -270,6 +324,7 @@ static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
   else
   {
     a.Uin = c->U, a.Uout = c->U, a.U0 = nullptr, a.Qout = c->Q[nxt], a.final_stage = 1;
+    set_peers(nxt);
     prof_mark(0);
     e = launch_sweep(c->tmapQ[cur], a, c->stream);
     prof_mark(1);
@@ -277,6 +332,8 @@ static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
       return cuda_fail(e, "sweep", __FILE__, __LINE__);
     c->cur = nxt;
   }
+  c->halo_gen++;
+  c->mail_gen++;
   c->acc_parity ^= 1;
   return FV2D_OK;
 }
@@ -287,7 +344,10 @@ static int compute_dt_now(fv2d_ctx *c)
   unsigned long long init = FV2D_ENC_NEG_MAX;
   FV2D_CUDA(cudaMemcpyAsync(&c->sc->inv_acc[c->acc_parity][0], &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
   launch_compute_dt(c->kp, c->Q[c->cur], &c->sc->inv_acc[c->acc_parity][0], c->stream);
-  launch_finalize_dt(c->kp, &c->sc->inv_acc[c->acc_parity][0], c->stream);
+  if (c->nranks > 1 && !c->connected)
+    return arg_fail("multi-GPU context: call fv2d_halo_connect before computing dt");
+  c->mail_gen++;
+  launch_finalize_dt(c->kp, &c->sc->inv_acc[c->acc_parity][0], c->mail_gen, c->stream);
   c->n_launch_total += 2;
   FV2D_CUDA(cudaGetLastError());
   return FV2D_OK;
@@ -429,6 +489,19 @@ int fv2d_ctx_create_slab(const fv2d_device_params *dev, int time_stepping, doubl
   kp.edge_lo = (rank == 0 && !(periodic_y && nranks > 1)) ? EDGE_PHYSICAL : EDGE_NEIGHBOUR;
   kp.edge_hi = (rank == nranks - 1 && !(periodic_y && nranks > 1)) ? EDGE_PHYSICAL : EDGE_NEIGHBOUR;
   kp.eps_reset = eps_reset_negative;
+  kp.rank      = rank;
+  kp.nranks    = nranks;
+  c->num_sms   = prop.multiProcessorCount;
+  if (nranks > kMaxRanks)
+  {
+    delete c;
+    return arg_fail("at most 8 y-slabs (one NVSwitch box) are supported");
+  }
+  if (nranks > 1 && Nyl < 2 * dev->Ng)
+  {
+    delete c;
+    return arg_fail("slab thinner than the ghost layer");
+  }
 
   Layout &L = kp.L;
   L.lead    = (16 - dev->ibeg % 16) % 16;
@@ -463,6 +536,9 @@ int fv2d_ctx_create_slab(const fv2d_device_params *dev, int time_stepping, doubl
   FV2D_TRY(cudaMallocHost(&c->sc_host, sizeof(DevScalars)));
   std::memset(c->sc_host, 0, sizeof(DevScalars));
   kp.sc = c->sc;
+  for (int q = 0; q < kMaxRanks; ++q)
+    kp.peer_sc[q] = nullptr;
+  kp.peer_sc[rank] = c->sc; // a single slab mails itself
 
   // analytical gravity profile: glibc sin() on the host, narrowed to float (Gravity.h:15-29, Q5)
   if (dev->gravity_mode == FV2D_GRAV_ANALYTICAL)
@@ -784,7 +860,7 @@ int fv2d_get_time(fv2d_ctx *c, double *t, double *next_dt, int64_t *steps)
   {
     // what step_begin would compute from the current accumulator
     const fv2d_device_params &p = c->kp.p;
-    double hyp = decode_ordered(c->sc_host->inv_acc[c->acc_parity][0]);
+    double hyp = current_hyp(c);
     double tc = p.epsilon, visc = p.epsilon;
     if (p.thermal_conductivity_active)
       tc = std::fmax(2.0 * p.kappa / (p.dx * p.dx), 2.0 * p.kappa / (p.dy * p.dy));
@@ -852,7 +928,7 @@ int fv2d_get_inv_dt(fv2d_ctx *c, double inv_dt[3])
     return rc;
   // maxima of the CURRENT state (what the next step's dt is made of), ComputeDt.h:30-52
   const fv2d_device_params &p = c->kp.p;
-  inv_dt[0] = decode_ordered(c->sc_host->inv_acc[c->acc_parity][0]);
+  inv_dt[0] = current_hyp(c);
   inv_dt[1] = p.epsilon;
   inv_dt[2] = p.epsilon;
   if (p.thermal_conductivity_active)
@@ -942,24 +1018,117 @@ int fv2d_advance_host(fv2d_ctx *c, const double *hostQ_in, double *hostQ_out, in
 
 // ------------------------------------------------------------------ multi-GPU halo exchange
 
+// What one rank publishes about its exchange buffers (fits FV2D_IPC_HANDLE_BYTES).
+struct HaloHandle
+{
+  uint32_t magic;
+  int32_t rank, nranks, device;
+  int64_t pid;
+  cudaIpcMemHandle_t mem[3]; // Q[0], Q[1], scalars
+  uint64_t offset[3];        // of the pointer inside its cudaMalloc allocation
+  uint64_t raw[3];           // same-process shortcut: the device pointers themselves
+};
+static_assert(sizeof(HaloHandle) <= FV2D_IPC_HANDLE_BYTES, "handle too large");
+
+typedef CUresult (*PFN_getAddressRange)(CUdeviceptr *, size_t *, CUdeviceptr);
+
 int fv2d_halo_export(fv2d_ctx *c, void *handle)
 {
   FV2D_ENTER(c);
-  (void)handle;
-  return arg_fail("halo exchange: not implemented yet");
+  if (!handle)
+    return arg_fail("null handle");
+  static PFN_getAddressRange getRange = nullptr;
+  if (!getRange)
+  {
+    void *fp = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    FV2D_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &qres));
+    getRange = (PFN_getAddressRange)fp;
+  }
+  HaloHandle h;
+  std::memset(&h, 0, sizeof h);
+  h.magic  = 0x46563244u;
+  h.rank   = c->rank;
+  h.nranks = c->nranks;
+  h.device = c->device;
+  h.pid    = (int64_t)getpid();
+  void *ptrs[3] = {c->Q[0], c->Q[1], c->sc};
+  for (int k = 0; k < 3; ++k)
+  {
+    FV2D_CUDA(cudaIpcGetMemHandle(&h.mem[k], ptrs[k]));
+    CUdeviceptr base = 0;
+    size_t size      = 0;
+    if (!getRange || getRange(&base, &size, (CUdeviceptr)ptrs[k]) != CUDA_SUCCESS)
+      base = (CUdeviceptr)ptrs[k];
+    h.offset[k] = (uint64_t)((CUdeviceptr)ptrs[k] - base);
+    h.raw[k]    = (uint64_t)(uintptr_t)ptrs[k];
+  }
+  std::memset(handle, 0, FV2D_IPC_HANDLE_BYTES);
+  std::memcpy(handle, &h, sizeof h);
+  return FV2D_OK;
 }
+
 int fv2d_halo_connect(fv2d_ctx *c, const void *handles, int nranks)
 {
   FV2D_ENTER(c);
-  (void)handles;
-  (void)nranks;
-  return arg_fail("halo exchange: not implemented yet");
-}
-int fv2d_halo_connect_local(fv2d_ctx **ctxs, int nranks)
-{
-  (void)ctxs;
-  (void)nranks;
-  return arg_fail("halo exchange: not implemented yet");
+  if (!handles || nranks != c->nranks)
+    return arg_fail("fv2d_halo_connect: need one handle per rank of this context's decomposition");
+  if (c->connected)
+    return arg_fail("fv2d_halo_connect: already connected");
+  const int lo = (c->rank + nranks - 1) % nranks, hi = (c->rank + 1) % nranks;
+  const bool need_lo = c->kp.edge_lo == EDGE_NEIGHBOUR, need_hi = c->kp.edge_hi == EDGE_NEIGHBOUR;
+  const int64_t mypid = (int64_t)getpid();
+  for (int q = 0; q < nranks; ++q)
+  {
+    HaloHandle h;
+    std::memcpy(&h, (const char *)handles + (size_t)q * FV2D_IPC_HANDLE_BYTES, sizeof h);
+    if (h.magic != 0x46563244u || h.rank != q || h.nranks != nranks)
+      return arg_fail("fv2d_halo_connect: malformed handle for rank " + std::to_string(q));
+    if (q == c->rank)
+    {
+      c->kp.peer_sc[q] = c->sc;
+      continue;
+    }
+    void *ptr[3] = {nullptr, nullptr, nullptr};
+    const bool want[3] = {(q == lo && need_lo) || (q == hi && need_hi), (q == lo && need_lo) || (q == hi && need_hi), true};
+    for (int k = 0; k < 3; ++k)
+    {
+      if (!want[k])
+        continue;
+      if (h.pid == mypid)
+      {
+        // same process (single-process multi-GPU driver / tests): plain peer access
+        if (h.device != c->device)
+        {
+          cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+            return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+          cudaGetLastError();
+        }
+        ptr[k] = (void *)(uintptr_t)h.raw[k];
+      }
+      else
+      {
+        void *base = nullptr;
+        FV2D_CUDA(cudaIpcOpenMemHandle(&base, h.mem[k], cudaIpcMemLazyEnablePeerAccess));
+        c->ipc_opened[c->n_ipc_opened++] = base;
+        ptr[k]                           = (char *)base + h.offset[k];
+      }
+    }
+    c->kp.peer_sc[q] = (DevScalars *)ptr[2];
+    if (q == lo && need_lo)
+    {
+      c->peerQ_lo[0] = (double *)ptr[0];
+      c->peerQ_lo[1] = (double *)ptr[1];
+    }
+    if (q == hi && need_hi)
+    {
+      c->peerQ_hi[0] = (double *)ptr[0];
+      c->peerQ_hi[1] = (double *)ptr[1];
+    }
+  }
+  c->connected = true;
+  return FV2D_OK;
 }
 
 } // extern "C"

@@ -34,6 +34,8 @@ struct Layout
   }
 };
 
+constexpr int kMaxRanks = 8; // y-slabs per job: the GPUs of one NVSwitch box
+
 // What lies beyond the low-j / high-j edge of the local slab.
 enum : int
 {
@@ -51,6 +53,12 @@ struct DevScalars
   unsigned long long neg[4];        // cumulative {rho<0, P<0, NaN, -}
   double inv_dt_last[4];            // decoded maxima behind `dt`
   double sums[2];                   // scratch for mass/energy integration
+  // ---- multi-GPU mailboxes: written by peers over NVLink (system-scope stores), read locally
+  unsigned long long halo_cnt[2];      // ghost-row pushes received from the low-j / high-j neighbour
+  unsigned long long mail_gen[kMaxRanks]; // per source rank: generation of its last CFL mail
+  double mail_inv[2][kMaxRanks];       // [generation parity][source rank]: that rank's max inverse dt
+  unsigned int cta_done;               // CTAs of the running sweep that have finished (local)
+  unsigned int fault;                  // set if a wait on a peer timed out
   double dt_hist[FV2D_DT_HISTORY];  // ring of dts used
 };
 
@@ -65,6 +73,8 @@ struct KParams
   double eps_reset;
   const double *gtab;    // per-local-row analytical gravity (float-valued), or nullptr
   DevScalars *sc;
+  int rank, nranks;
+  DevScalars *peer_sc[kMaxRanks]; // every rank's scalars, mapped into this device (self included)
 };
 
 // Monotone map double -> uint64 so that atomicMax on the integer orders like the double.
@@ -93,6 +103,72 @@ __host__ __device__ inline double decode_ordered(unsigned long long e)
 #define FV2D_ENC_NEG_MAX 0x0010000000000000ULL
 constexpr int kProfMax = 8192;
 
+#ifdef __CUDACC__
+// ---- system-scope (cross-GPU, over NVLink peer mappings) flag primitives
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double *p, double v)
+{
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double *p)
+{
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+// Spin until *p >= v.  A peer that never answers must not hang the GPU: after ~20 s the wait
+// gives up and raises the context's fault flag (every host-synchronising call reports it).
+__device__ __forceinline__ bool wait_ge_sys(const unsigned long long *p, unsigned long long v, DevScalars *sc)
+{
+  if (ld_acquire_sys(p) >= v)
+    return true;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (ld_acquire_sys(p) < v)
+  {
+    __nanosleep(64);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 20000000000ULL)
+    {
+      sc->fault = 1;
+      return false;
+    }
+  }
+  return true;
+}
+
+// Posts this rank's maximum inverse time-step to every rank's mailbox (self included) and
+// stamps it with generation `gen`.  Called by exactly one thread per reduction.
+__device__ __forceinline__ void post_cfl_mail(const KParams &kp, double hyp, unsigned long long gen)
+{
+  for (int q = 0; q < kp.nranks; ++q)
+    st_relaxed_sys_f64(&kp.peer_sc[q]->mail_inv[gen & 1][kp.rank], hyp);
+  __threadfence_system();
+  for (int q = 0; q < kp.nranks; ++q)
+    st_release_sys(&kp.peer_sc[q]->mail_gen[kp.rank], gen);
+}
+// Waits for generation `gen` of every rank's mail and returns the global maximum.
+__device__ __forceinline__ double collect_cfl_mail(const KParams &kp, unsigned long long gen)
+{
+  double m = -1.7976931348623157e308;
+  for (int q = 0; q < kp.nranks; ++q)
+  {
+    wait_ge_sys(&kp.sc->mail_gen[q], gen, kp.sc);
+    m = fmax(m, ld_relaxed_sys_f64(&kp.sc->mail_inv[gen & 1][q]));
+  }
+  return m;
+}
+#endif
+
 void set_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 
@@ -113,6 +189,7 @@ struct fv2d_ctx
   fv2d_device_params glob; // global grid
   int time_stepping;
   int device;
+  int num_sms;
   int rank, nranks;
   cudaStream_t stream;
   bool own_stream;
@@ -138,10 +215,11 @@ struct fv2d_ctx
   int prof_n;           // pairs recorded
   long long n_launch_sweep, n_launch_total;
 
-  // multi-GPU peers (slab above / below)
-  double *peerQ_lo[2], *peerQ_hi[2]; // neighbour's Q[0], Q[1] (mapped through IPC / peer access)
-  fv2d::DevScalars *peer_sc[8];
+  // multi-GPU peers (slab below / above): the neighbours' Q[0], Q[1] mapped into this device
+  double *peerQ_lo[2], *peerQ_hi[2];
   void *ipc_opened[24];
   int n_ipc_opened;
   bool connected;
+  unsigned long long halo_gen; // sweeps whose edge rows have been pushed so far (same on all ranks)
+  unsigned long long mail_gen; // CFL reductions done so far (same on all ranks)
 };

@@ -13,7 +13,7 @@ void launch_prim_to_cons(const KParams &kp, const double *Q, double *U, cudaStre
 void launch_cons_to_prim(const KParams &kp, const double *U, double *Q, cudaStream_t s);
 void launch_check_negatives(const KParams &kp, double *Q, unsigned long long *counts, cudaStream_t s);
 void launch_compute_dt(const KParams &kp, const double *Q, unsigned long long *acc, cudaStream_t s);
-void launch_finalize_dt(const KParams &kp, const unsigned long long *acc, cudaStream_t s);
+void launch_finalize_dt(const KParams &kp, const unsigned long long *acc, unsigned long long mail_gen, cudaStream_t s);
 void launch_compute_slopes(const KParams &kp, const double *Q, double *sX, double *sY, cudaStream_t s);
 void launch_fluxes_and_update(const KParams &kp, const double *Q, const double *sX, const double *sY, double *Unew,
                               double dt, cudaStream_t s);
@@ -32,6 +32,8 @@ struct StepBeginArgs
   int acc_read;  // inv_acc slot holding the maxima of the CURRENT state
   int acc_reset; // inv_acc slot the coming sweep accumulates into (reset here)
   int advance;   // 1: t += dt, step++, dt history (once per time step); 0: ghost fill only
+  unsigned long long mail_gen;      // generation of the CFL mails that make up this step's dt
+  unsigned long long halo_expected; // ghost-row pushes each neighbour must have delivered by now
 };
 void launch_step_begin(const KParams &kp, double *Q, const StepBeginArgs &a, cudaStream_t s);
 
@@ -48,6 +50,11 @@ struct SweepArgs
   int acc_slot;    // inv_acc slot to atomically max into (final stage)
   int chunk_rows;  // rows per CTA work item
   int n_strips;
+  // multi-GPU: the neighbours' copy of Qout (peer-mapped), or nullptr at a physical edge.  The
+  // stage epilogue stores its two edge rows straight into the neighbour's ghost rows.
+  double *peer_lo_Qout, *peer_hi_Qout;
+  int lo_rank, hi_rank;
+  unsigned long long mail_gen; // generation stamped on this sweep's CFL mail (final stage)
 };
 // tmapQ must describe the array the stage READS (Qin).  Returns cudaSuccess or the launch error;
 // sets *launches to the number of kernels enqueued.

@@ -229,10 +229,12 @@ __host__ __device__ inline void parabolic_inv_dt(const fv2d_device_params &p, do
     visc = fmax(2.0 * p.mu / (p.dx * p.dx), 2.0 * p.mu / (p.dy * p.dy));
 }
 
-// dt = CFL / max({hyp, tc, visc})  (ComputeDt.h:64)
-__global__ void k_finalize_dt(KParams kp, const unsigned long long *__restrict__ acc)
+// dt = CFL / max({hyp, tc, visc})  (ComputeDt.h:64).  The hyperbolic maximum is reduced over
+// all y-slabs through the peer mailboxes (a single slab mails itself).
+__global__ void k_finalize_dt(KParams kp, const unsigned long long *__restrict__ acc, unsigned long long mail_gen)
 {
-  double hyp = decode_ordered(acc[0]);
+  post_cfl_mail(kp, decode_ordered(acc[0]), mail_gen);
+  double hyp = collect_cfl_mail(kp, mail_gen);
   double tc, visc;
   parabolic_inv_dt(kp.p, tc, visc);
   double m = hyp;
@@ -553,9 +555,9 @@ void launch_compute_dt(const KParams &kp, const double *Q, unsigned long long *a
 {
   k_compute_dt<<<grid2d(kp.p.Nx, kp.p.Ny, kBlk), kBlk, 0, s>>>(kp, Q, acc);
 }
-void launch_finalize_dt(const KParams &kp, const unsigned long long *acc, cudaStream_t s)
+void launch_finalize_dt(const KParams &kp, const unsigned long long *acc, unsigned long long mail_gen, cudaStream_t s)
 {
-  k_finalize_dt<<<1, 1, 0, s>>>(kp, acc);
+  k_finalize_dt<<<1, 1, 0, s>>>(kp, acc, mail_gen);
 }
 void launch_compute_slopes(const KParams &kp, const double *Q, double *sX, double *sY, cudaStream_t s)
 {

@@ -263,7 +263,12 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
   const int strip = blockIdx.x;
   const int i0    = p.ibeg + strip * W; // first interior column of the strip
   const int col   = i0 - 2 + t;         // this thread's column
-  const int j0    = p.jbeg + blockIdx.y * a.chunk_rows;
+  // chunk order: when the slab has neighbours the two edge chunks are dispatched first, so
+  // their ghost-row pushes travel over NVLink while the interior chunks compute
+  int cy = blockIdx.y;
+  if ((a.peer_lo_Qout != nullptr || a.peer_hi_Qout != nullptr) && gridDim.y > 1)
+    cy = (cy == 0) ? 0 : (cy == 1 ? (int)gridDim.y - 1 : cy - 1);
+  const int j0    = p.jbeg + cy * a.chunk_rows;
   const int j1    = min(j0 + a.chunk_rows, p.jend); // rows [j0, j1) are updated
   const int rbase = j0 - 2;                         // first row staged
   const int rlast = j1 + 1;                         // last row staged
@@ -644,6 +649,22 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
 #pragma unroll
         for (int f = 0; f < 4; ++f)
           a.Qout[o + f * L.plane] = qo[f];
+        // multi-GPU: the slab's two edge rows are also the neighbour's ghost rows — store them
+        // straight into the neighbour's memory (peer mapping over NVLink)
+        if (a.peer_lo_Qout != nullptr && k < p.jbeg + 2)
+        {
+          const long long op = ocol + (long long)(p.Ny + k) * L.pitch; // its high ghost rows
+#pragma unroll
+          for (int f = 0; f < 4; ++f)
+            a.peer_lo_Qout[op + f * L.plane] = qo[f];
+        }
+        if (a.peer_hi_Qout != nullptr && k >= p.jend - 2)
+        {
+          const long long op = ocol + (long long)(k - p.Ny) * L.pitch; // its low ghost rows
+#pragma unroll
+          for (int f = 0; f < 4; ++f)
+            a.peer_hi_Qout[op + f * L.plane] = qo[f];
+        }
       }
     }
 
@@ -657,6 +678,25 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
     {
       qk[f] = qn[f];
       qn[f] = qnn[f];
+    }
+  }
+
+  // ---- multi-GPU: tell the neighbours how many of their ghost rows this CTA has delivered
+  if (a.peer_lo_Qout != nullptr || a.peer_hi_Qout != nullptr)
+  {
+    const int n_lo = (a.peer_lo_Qout != nullptr) ? max(0, min(j1, p.jbeg + 2) - j0) : 0;
+    const int n_hi = (a.peer_hi_Qout != nullptr) ? max(0, j1 - max(j0, p.jend - 2)) : 0;
+    if (n_lo + n_hi > 0)
+    {
+      __threadfence_system();
+      __syncthreads();
+      if (t == 0)
+      {
+        if (n_lo)
+          atomicAdd_system(&a.kp.peer_sc[a.lo_rank]->halo_cnt[1], (unsigned long long)n_lo);
+        if (n_hi)
+          atomicAdd_system(&a.kp.peer_sc[a.hi_rank]->halo_cnt[0], (unsigned long long)n_hi);
+      }
     }
   }
 
@@ -675,14 +715,6 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
     double *red = &S.X2[0][0][0];
     if ((t & 31) == 0)
       red[t >> 5] = inv_dt_max;
-    __syncthreads();
-    if (t == 0)
-    {
-      double m = red[0];
-      for (int w = 1; w < NT / 32; ++w)
-        m = fmax(m, red[w]);
-      atomicMax(&a.kp.sc->inv_acc[a.acc_slot][0], encode_ordered(m));
-    }
     if ((t & 31) == 0)
     {
       if (n_negr)
@@ -691,6 +723,25 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
         atomicAdd(&a.kp.sc->neg[1], (unsigned long long)n_negp);
       if (n_nan)
         atomicAdd(&a.kp.sc->neg[2], (unsigned long long)n_nan);
+    }
+    __syncthreads();
+    if (t == 0)
+    {
+      double m = red[0];
+      for (int w = 1; w < NT / 32; ++w)
+        m = fmax(m, red[w]);
+      DevScalars *sc = a.kp.sc;
+      atomicMax(&sc->inv_acc[a.acc_slot][0], encode_ordered(m));
+      // the last CTA of the sweep mails the slab's maximum to every rank (self included):
+      // the next step's dt is reduced on the device, no host round trip
+      __threadfence();
+      const unsigned prev = atomicAdd(&sc->cta_done, 1u);
+      if (prev == gridDim.x * gridDim.y - 1)
+      {
+        sc->cta_done                 = 0;
+        const unsigned long long enc = atomicMax(&sc->inv_acc[a.acc_slot][0], 0ULL);
+        post_cfl_mail(a.kp, decode_ordered(enc), a.mail_gen);
+      }
     }
   }
 }
@@ -725,7 +776,7 @@ __global__ void k_step_begin(KParams kp, double *__restrict__ Q, StepBeginArgs a
       double dt;
       if (a.use_device_dt)
       {
-        const double hyp = decode_ordered(sc->inv_acc[a.acc_read][0]);
+        const double hyp = collect_cfl_mail(kp, a.mail_gen);
         double tc = p.epsilon, visc = p.epsilon;
         if (p.thermal_conductivity_active)
           tc = fmax(2.0 * p.kappa / (p.dx * p.dx), 2.0 * p.kappa / (p.dy * p.dy));
@@ -774,10 +825,20 @@ __global__ void k_step_begin(KParams kp, double *__restrict__ Q, StepBeginArgs a
   bool flip_u = false, flip_v = false;
   if (j < p.jbeg || j >= p.jend)
   {
-    if (((j < p.jbeg) ? kp.edge_lo : kp.edge_hi) != EDGE_PHYSICAL)
-      return;
-    js     = bc_src(p.boundary_y, j, p.jbeg, p.jend, p.Ny);
-    flip_v = (p.boundary_y == FV2D_BC_REFLECTING);
+    const int side = (j < p.jbeg) ? 0 : 1;
+    if ((side == 0 ? kp.edge_lo : kp.edge_hi) != EDGE_PHYSICAL)
+    {
+      // ghost rows owned by the halo exchange: the neighbour pushed the domain columns; once
+      // they have all arrived, apply the x boundary condition to the row's own x-ghosts
+      if (i >= p.ibeg && i < p.iend)
+        return;
+      wait_ge_sys(&kp.sc->halo_cnt[side], a.halo_expected, kp.sc);
+    }
+    else
+    {
+      js     = bc_src(p.boundary_y, j, p.jbeg, p.jend, p.Ny);
+      flip_v = (p.boundary_y == FV2D_BC_REFLECTING);
+    }
   }
   if (i < p.ibeg || i >= p.iend)
   {

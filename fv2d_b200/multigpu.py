@@ -1,0 +1,65 @@
+"""One-process-per-GPU plumbing for the y-slab decomposition.
+
+torch.distributed is used for exactly two things: telling ranks apart and all-gathering the
+512-byte exchange handles once at start-up.  After `connect`, every per-step exchange (ghost
+rows, the global CFL reduction) happens inside the CUDA kernels over NVLink peer mappings;
+no collective is called per step.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import capi
+
+
+def slab_rows(Ny: int, Ng: int, rank: int, nranks: int):
+    """(first local row in the global array incl. ghosts, number of local rows incl. ghosts)
+    of y-slab `rank`: owned rows [rank*Ny/nranks, (rank+1)*Ny/nranks) plus Ng ghost rows a side."""
+    if Ny % nranks:
+        raise ValueError("Ny must be divisible by the number of slabs")
+    nyl = Ny // nranks
+    return rank * nyl, nyl + 2 * Ng
+
+
+def split_global(Qglobal: np.ndarray, Ng: int, rank: int, nranks: int) -> np.ndarray:
+    """The local slab (with its ghost rows, taken from the neighbours' rows) of a global
+    [f][Nty][Ntx] array whose ghosts are already filled."""
+    Ny = Qglobal.shape[1] - 2 * Ng
+    j0, n = slab_rows(Ny, Ng, rank, nranks)
+    return np.ascontiguousarray(Qglobal[:, j0:j0 + n, :])
+
+
+def join_slabs(slabs, Ng: int) -> np.ndarray:
+    """Inverse of split_global for the domain rows (ghost rows of the result are the outer
+    slabs' own ghost rows)."""
+    parts = [s[:, Ng:-Ng, :] for s in slabs]
+    return np.concatenate([slabs[0][:, :Ng, :]] + parts + [slabs[-1][:, -Ng:, :]], axis=1)
+
+
+def gather_handles(local: bytes, dist, device=None) -> bytes:
+    """all_gather of the per-rank exchange handles (works with the nccl and the gloo backend)."""
+    import torch
+
+    world = dist.get_world_size()
+    mine = torch.tensor(list(local), dtype=torch.uint8, device=device)
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine)
+    return b"".join(bytes(t.cpu().tolist()) for t in out)
+
+
+def connect(ctx: "capi.Context", dist) -> None:
+    """Exchange IPC handles and map the neighbours' buffers (call once, collectively)."""
+    import torch
+
+    world = dist.get_world_size()
+    device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else None
+    handles = gather_handles(ctx.halo_export(), dist, device)
+    ctx.halo_connect(handles, world)
+    dist.barrier()
+
+
+def connect_local(ctxs) -> None:
+    """Single-process variant: contexts on several GPUs of this process."""
+    handles = b"".join(c.halo_export() for c in ctxs)
+    for c in ctxs:
+        c.halo_connect(handles, len(ctxs))

@@ -169,17 +169,19 @@ int fv2d_advance_host(fv2d_ctx *ctx, const double *hostQ_in, double *hostQ_out, 
  * peer memory (CUDA IPC): every rank publishes a handle to its Q buffers, opens its two
  * y-neighbours' handles, and the stage epilogue's edge rows are written straight into the
  * neighbour's ghost rows. */
-#define FV2D_IPC_HANDLE_BYTES 256
+#define FV2D_IPC_HANDLE_BYTES 512
 /* Fills `handle` (FV2D_IPC_HANDLE_BYTES bytes) describing this rank's exchange buffers. */
 int fv2d_halo_export(fv2d_ctx *ctx, void *handle);
 /* handles: nranks consecutive handles gathered from all ranks (e.g. torch.distributed
  * all_gather), index = rank. */
 int fv2d_halo_connect(fv2d_ctx *ctx, const void *handles, int nranks);
-/* Same-process variant (tests, single-process multi-GPU drivers). */
-int fv2d_halo_connect_local(fv2d_ctx **ctxs, int nranks);
-/* Global dt across ranks: each rank writes its three inverse-dt maxima into every peer's
- * mailbox from the stage epilogue; the next step's prologue reduces them.  Nothing to call
- * per step — these are here for diagnostics. */
+/* (Handles from contexts of the SAME process are recognised and connected through plain
+ * peer access instead of IPC.)  All ranks must stay alive, and must not destroy their
+ * context, while any rank is still stepping.
+ * Global dt across ranks: the last CTA of each rank's final-stage sweep writes the slab's
+ * maximum inverse dt into every rank's mailbox; the next step's prologue reduces them on the
+ * device.  Nothing to call per step.
+ * fv2d_get_inv_dt: the three inverse-dt maxima {hyp, tc, visc} of the CURRENT state. */
 int fv2d_get_inv_dt(fv2d_ctx *ctx, double inv_dt[3]);
 
 #ifdef __cplusplus

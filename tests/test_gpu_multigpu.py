@@ -1,0 +1,94 @@
+"""y-slab decomposition over several GPUs of one box (needs >= 2 GPUs; skipped otherwise).
+The contract: the N-GPU result is BITWISE the 1-GPU result — face fluxes
+depend only on local stencil values and Max is associative."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from fv2d_b200 import capi, multigpu
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    import torch
+
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def _single(dev, run, Q0, n):
+    with capi.Context(dev, run.time_stepping, run.epsilon_reset_negative) as ctx:
+        ctx.upload_Q(Q0)
+        ctx.prim_to_cons()
+        ctx.compute_dt()
+        ctx.run_steps(n)
+        return ctx.download_Q(), ctx.download_U(), ctx.dt_history(n)
+
+
+def _multi(dev, run, Q0, n, nranks):
+    ctxs = [capi.Context(dev, run.time_stepping, run.epsilon_reset_negative, device=r, rank=r, nranks=nranks)
+            for r in range(nranks)]
+    try:
+        multigpu.connect_local(ctxs)
+        for r, c in enumerate(ctxs):
+            c.upload_Q(multigpu.split_global(Q0, dev.Ng, r, nranks))
+            c.prim_to_cons()
+        # compute_dt is collective and synchronises the host: one thread per rank
+        _compute_dt_all(ctxs)
+        for c in ctxs:
+            c.run_steps(n)
+        Qs = [c.download_Q() for c in ctxs]
+        Us = [c.download_U() for c in ctxs]
+        dts = [c.dt_history(n) for c in ctxs]
+        return multigpu.join_slabs(Qs, dev.Ng), multigpu.join_slabs(Us, dev.Ng), dts
+    finally:
+        for c in ctxs:
+            c.sync()
+        for c in ctxs:
+            c.close()
+
+
+def _compute_dt_all(ctxs):
+    """fv2d_compute_dt is collective and host-synchronous: call it from one thread per rank."""
+    import threading
+
+    out = [None] * len(ctxs)
+
+    def work(k):
+        out[k] = ctxs[k].compute_dt()[0]
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(len(ctxs))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    return out
+
+
+CASES = [
+    ("kh_plm_128x64", {"mesh.Nx": 777, "mesh.Ny": 336}),     # periodic-x / absorbing-y, 4 strips
+    ("blast_64", {"mesh.Nx": 300, "mesh.Ny": 296}),          # periodic-y: the exchange is a ring
+    ("gresho_rk2_32", {"mesh.Nx": 260, "mesh.Ny": 128}),     # RK2: two exchanges per step
+    ("c91_64x32", {"mesh.Nx": 256, "mesh.Ny": 128}),         # gravity + WB flux at the GLOBAL edges + TC + viscosity
+    ("rt_plm_32x96", {"mesh.Nx": 64, "mesh.Ny": 192}),       # reflecting, gravity
+]
+
+
+@pytest.mark.parametrize("name,ov", CASES)
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_n_gpu_result_is_bitwise_the_1_gpu_result(name, ov, nranks):
+    if _ngpu() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    dev, run = capi.params_from_ini(load_golden(name).ini_path(), ov)
+    if dev.Ny % nranks:
+        pytest.skip("Ny not divisible")
+    Q0 = capi.init_problem(dev, run)
+    n = 8
+    Q1, U1, dts1 = _single(dev, run, Q0, n)
+    Qn, Un, dtsn = _multi(dev, run, Q0, n, nranks)
+    for d in dtsn:
+        assert np.array_equal(d, dts1)
+    J = slice(dev.jbeg, dev.jend)
+    I = slice(dev.ibeg, dev.iend)
+    assert np.array_equal(Un[:, J, I], U1[:, J, I])
+    assert np.array_equal(Qn[:, J, I], Q1[:, J, I])

@@ -161,29 +161,33 @@ def test_check_negatives_on_device():
 
 
 def test_fused_negative_reset_and_counters():
-    """A step that drives a cell negative: the fused epilogue must reset Q (not U) and count,
-    exactly like consToPrim + checkNegatives (SimInfo.h:602-646)."""
+    """Steps that drive cells negative (violent expansion, dt 12x the CFL limit): the fused
+    epilogue must reset Q (not U) and count exactly like consToPrim + checkNegatives
+    (SimInfo.h:602-646)."""
     g = load_golden("blast_64")
     dev, run, Q0 = _setup(g)
     Q0 = Q0.copy()
-    # a near-vacuum cell next to the blast: the first step undershoots
-    Q0[3, dev.jbeg + 30, dev.ibeg + 30] = 1e-9
-    Q0[0, dev.jbeg + 31, dev.ibeg + 31] = 1e-9
-    dev2 = dev.copy()
-    dev2.CFL = 0.9
-    Qo, Uo = Q0.copy(), O.prim_to_cons(dev2, Q0)
-    n, t, dts, neg_o = O.run(dev2, run.time_stepping, run.epsilon_reset_negative, 1e9, Qo, Uo, 3)
-    with capi.Context(dev2, run.time_stepping, run.epsilon_reset_negative) as ctx:
+    mid = dev.ibeg + dev.Nx // 2
+    Q0[1, :, mid:], Q0[1, :, :mid], Q0[3] = 4.0, -4.0, 0.05
+    O.fill_boundaries(dev, Q0)
+    eps = run.epsilon_reset_negative
+    dt = 12.0 * O.compute_dt(dev, Q0)[0]
+    Qo, Uo, neg_o = Q0.copy(), O.prim_to_cons(dev, Q0), [0, 0, 0]
+    for _ in range(3):
+        O.update(dev, run.time_stepping, Qo, Uo, dt)
+        Qo = O.cons_to_prim(dev, Uo)
+        neg_o = [x + y for x, y in zip(neg_o, O.check_negatives(dev, eps, Qo))]
+    with capi.Context(dev, run.time_stepping, eps) as ctx:
         ctx.upload_Q(Q0)
         ctx.prim_to_cons()
-        ctx.compute_dt()
-        ctx.run_steps(3)
+        for _ in range(3):
+            ctx.step(dt)
         neg = ctx.negative_counts()
-        Q = ctx.download_Q()
-    assert sum(neg_o) > 0, "test setup should trigger resets"
+        Q, U = ctx.download_Q(), ctx.download_U()
+    assert neg_o[0] > 0 and neg_o[1] > 0, "test setup should trigger resets"
     assert neg == neg_o
-    assert np.array_equal(O.domain(dev2, Q) == run.epsilon_reset_negative,
-                          O.domain(dev2, Qo) == run.epsilon_reset_negative)
+    assert np.array_equal(O.domain(dev, Q) == eps, O.domain(dev, Qo) == eps)
+    assert rel_l1(O.domain(dev, U), O.domain(dev, Uo)) <= 1e-11  # U is not reset (SimInfo.h:614-627)
 
 
 def test_run_until_replays_the_reference_loop_condition():
@@ -222,7 +226,7 @@ def test_cpp_host_driver_runs_the_reference_loop(tmp_path):
         r = subprocess.run([str(exe), g.ini_path(), "--max-steps", "10"] + mode, cwd=tmp_path, capture_output=True,
                            text=True)
         assert r.returncode == 0, r.stderr
-        assert "Computing dts at (t=0) : dt_hyp=0.000968246" in r.stdout
+        assert "Computing dts at (t=0) : dt_hyp=0.00968246" in r.stdout
         outs[bool(mode)] = r.stdout
         snaps = sorted(tmp_path.glob("run_*.bin"))
         assert snaps, "no snapshot written"
