@@ -14,7 +14,7 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libfv2d_b200.so"
+LIB_PATH = Path(os.environ.get("FV2D_B200_LIB", _HERE / "libfv2d_b200.so"))
 
 FV2D_DT_HISTORY = 4096
 FV2D_IPC_HANDLE_BYTES = 512

@@ -68,6 +68,14 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, 
                : "memory");
 }
 
+// Asks the L2 to fetch `bytes` (multiple of 16) starting at the 16-byte aligned `ptr`
+// (SASS: UBLKPF).  Used to pull the U rows a few rows ahead of the sweep so the later
+// per-thread loads hit in L2 instead of paying the loaded-HBM latency.
+__device__ __forceinline__ void l2_prefetch(const void *ptr, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+}
+
 // Predicated fp64 global load issued HERE (asm volatile keeps it above the row barrier), so
 // the HBM latency overlaps the whole row of arithmetic instead of stalling the first use.
 __device__ __forceinline__ double ldg_stream(const double *ptr, int pred)
@@ -346,6 +354,18 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
 
   const long long ocol = L.at(0, col, 0);
   const double *Ucol   = a.Uin + ocol;
+  // U rows are pulled into L2 kUAhead rows ahead of their use (one bulk prefetch per field)
+  constexpr int kUAhead     = 3;
+  const int ncols_strip     = min(W, p.iend - i0) & ~1;
+  const uint32_t upf_bytes  = (uint32_t)ncols_strip * (uint32_t)sizeof(double);
+  const double *Ustrip      = a.Uin + L.at(0, i0, 0);
+  if (t == 0 && upf_bytes > 0)
+  {
+    for (int r = j0; r < min(j0 + kUAhead, j1); ++r)
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+        l2_prefetch(Ustrip + f * L.plane + (long long)r * L.pitch, upf_bytes);
+  }
 
   double inv_dt_max = -1.7976931348623157e308;
   unsigned n_negr = 0, n_negp = 0, n_nan = 0;
@@ -468,6 +488,13 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
         const int s = slot_of(rnew);
         mbar_expect_tx(&S.full[s], kRowBytes);
         tma_load_3d(&S.ring[s][0][0], &tmQ, tma_x, rnew, 0, &S.full[s]);
+      }
+      const int rpf = k + 1 + kUAhead;
+      if (rpf < j1 && upf_bytes > 0)
+      {
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+          l2_prefetch(Ustrip + f * L.plane + (long long)rpf * L.pitch, upf_bytes);
       }
     }
 
@@ -861,7 +888,10 @@ void launch_step_begin(const KParams &kp, double *Q, const StepBeginArgs &a, cud
 
 // --------------------------------------------------------------------------- dispatch
 
-constexpr int kNT = 256;
+#ifndef FV2D_NT
+#define FV2D_NT 256
+#endif
+constexpr int kNT = FV2D_NT;
 int sweep_strip_width() { return kNT - 4; }
 
 template <bool PLM, int SOLVER, bool GRAV, bool DIFF>
