@@ -194,17 +194,16 @@ def native_arm(args):
     dev, run = capi.params_from_ini(ROOT / "settings" / base, ov)
     Nx, Ny = dev.Nx, dev.Ny
 
-    # synthetic initial condition from the reference's own init function, on the host
-    t_init = time.perf_counter()
-    Qfull = capi.init_problem(dev, run)
-    t_init = time.perf_counter() - t_init
-
     ctx = capi.Context(dev, run.time_stepping, run.epsilon_reset_negative, device=local_rank, rank=rank, nranks=world)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
     Nyl, joff = ctx.Ny, ctx.j_offset
-    Qloc = np.ascontiguousarray(Qfull[:, joff:joff + Nyl + 2 * dev.Ng, :])
-    del Qfull
+    # synthetic initial condition from the reference's own init function, on the host; each
+    # rank evaluates only the rows of its own y-slab (+ ghost rows)
+    os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
+    t_init = time.perf_counter()
+    Qloc = capi.init_problem_rows(dev, run, joff, Nyl + 2 * dev.Ng)
+    t_init = time.perf_counter() - t_init
     if world > 1:
         from fv2d_b200 import multigpu
 

@@ -149,6 +149,7 @@ def lib() -> C.CDLL:
         "fv2d_params_from_ini": [C.c_char_p, C.c_char_p, C.POINTER(DeviceParams), C.POINTER(RunParams)],
         "fv2d_params_dump_ini": [C.c_char_p, C.c_char_p, C.c_char_p],
         "fv2d_init_problem": [C.POINTER(DeviceParams), C.POINTER(RunParams), _dp],
+        "fv2d_init_problem_rows": [C.POINTER(DeviceParams), C.POINTER(RunParams), C.c_int, C.c_int, _dp],
         "fv2d_ctx_create": [C.POINTER(DeviceParams), C.c_int, C.c_double, C.c_int, C.POINTER(_ctxp)],
         "fv2d_ctx_create_slab": [C.POINTER(DeviceParams), C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(_ctxp)],
         "fv2d_ctx_set_stream": [_ctxp, C.c_void_p],
@@ -229,6 +230,13 @@ def init_problem(dev: DeviceParams, run: RunParams) -> np.ndarray:
     """InitFunctor(params).init(Q) of the reference (Init.h:310-358); returns Q[f][j][i]."""
     Q = np.zeros(dev.shape(), dtype=np.float64)
     _check(lib().fv2d_init_problem(C.byref(dev), C.byref(run), _ptr(Q)))
+    return Q
+
+
+def init_problem_rows(dev: DeviceParams, run: RunParams, j_first: int, nrows: int) -> np.ndarray:
+    """Rows [j_first, j_first+nrows) of init_problem(dev, run), ghosts included."""
+    Q = np.zeros((4, nrows, dev.Ntx), dtype=np.float64)
+    _check(lib().fv2d_init_problem_rows(C.byref(dev), C.byref(run), j_first, nrows, _ptr(Q)))
     return Q
 
 

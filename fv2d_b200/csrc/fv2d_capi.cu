@@ -437,6 +437,32 @@ int fv2d_init_problem(const fv2d_device_params *dev, const fv2d_run_params *run,
   return FV2D_OK;
 }
 
+int fv2d_init_problem_rows(const fv2d_device_params *dev, const fv2d_run_params *run, int j_first, int nrows,
+                           double *hostQ_rows)
+{
+  if (!dev || !run || !hostQ_rows)
+    return arg_fail("null argument");
+  if (j_first < 0 || nrows < 1 || j_first + nrows > dev->Nty)
+    return arg_fail("row window outside the grid");
+  try
+  {
+    Params prm;
+    static_cast<fv2d_device_params &>(prm.device_params) = *dev;
+    prm.problem                                           = run->problem;
+    prm.seed                                              = run->seed;
+    InitFunctor init(prm);
+    HostArray Q(nrows, dev->Ntx);
+    init.init_rows(Q, j_first);
+    std::memcpy(hostQ_rows, Q.data.data(), Q.data.size() * sizeof(double));
+  }
+  catch (const std::exception &e)
+  {
+    set_error(e.what());
+    return FV2D_ERR_CONFIG;
+  }
+  return FV2D_OK;
+}
+
 int fv2d_ctx_create_slab(const fv2d_device_params *dev, int time_stepping, double eps_reset_negative, int device,
                          int rank, int nranks, fv2d_ctx **out)
 {

@@ -61,6 +61,12 @@ int fv2d_params_dump_ini(const char *ini_path, const char *overrides, const char
  * hostQ: zero-filled on entry by this function, then domain + ghosts are written. */
 int fv2d_init_problem(const fv2d_device_params *dev, const fv2d_run_params *run, double *hostQ);
 
+/* Rows [j_first, j_first + nrows) of the array fv2d_init_problem would produce (ghost cells
+ * included), layout [f][nrows][Ntx]: lets each rank of a multi-GPU job initialise only its
+ * own y-slab. */
+int fv2d_init_problem_rows(const fv2d_device_params *dev, const fv2d_run_params *run, int j_first, int nrows,
+                           double *hostQ_rows);
+
 /* ------------------------------------------------------------------ context */
 
 /* Allocates Q and U (zero-filled, like Kokkos Views: main.cpp:33-34) on CUDA device
