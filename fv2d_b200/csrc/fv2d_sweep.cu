@@ -120,6 +120,12 @@ __device__ __forceinline__ double csound(double gp, double rho)
   return (gp + gp) * h;
 }
 
+// max / min as one DSETP + two FSEL.  fmax()/fmin() lower to ~8 instructions each on sm_100a
+// (NaN-propagation fix-ups); the operands here are never NaN unless the state already is, and
+// then the NaN is counted by the epilogue either way.
+__device__ __forceinline__ double dmax(double a, double b) { return (a > b) ? a : b; }
+__device__ __forceinline__ double dmin(double a, double b) { return (a < b) ? a : b; }
+
 // minmod (Update.h:69-85), branch-free
 __device__ __forceinline__ double minmod_f(double dL, double dR)
 {
@@ -143,9 +149,10 @@ struct FaceFlux
 //   SL > 0 -> left state; else uS > 0 -> left star; else SR > 0 -> right star; else right.
 __device__ __forceinline__ FaceFlux hllc_f(const FaceState &L, const FaceState &R, double entho)
 {
-  const double cmax = fmax(L.c, R.c);
-  const double SL   = fmin(L.n, R.n) - cmax;
-  const double SR   = fmax(L.n, R.n) + cmax;
+  const double cmax = dmax(L.c, R.c);
+  const bool lt     = L.n < R.n; // one compare serves min and max
+  const double SL   = (lt ? L.n : R.n) - cmax;
+  const double SR   = (lt ? R.n : L.n) + cmax;
 
   const double rcL = L.r * (L.n - SL);
   const double rcR = R.r * (SR - R.n);
@@ -185,8 +192,8 @@ __device__ __forceinline__ FaceFlux hllc_f(const FaceState &L, const FaceState &
 // HLL with Davis speeds (RiemannSolvers.h:7-51)
 __device__ __forceinline__ FaceFlux hll_f(const FaceState &L, const FaceState &R, double entho)
 {
-  const double SL = fmin(L.n - L.c, R.n - R.c);
-  const double SR = fmax(L.n + L.c, R.n + R.c);
+  const double SL = dmin(L.n - L.c, R.n - R.c);
+  const double SR = dmax(L.n + L.c, R.n + R.c);
 
   const double mL = L.r * L.n, mR = R.r * R.n;
   const double EL = 0.5 * L.r * (L.n * L.n + L.t * L.t) + L.p * entho;
@@ -216,8 +223,8 @@ __device__ __forceinline__ FaceFlux hll_f(const FaceState &L, const FaceState &R
 // FSLP (RiemannSolvers.h:137-171)
 __device__ __forceinline__ FaceFlux fslp_f(const FaceState &L, const FaceState &R, double entho, double gdx, double K)
 {
-  const double ai    = K * fmax(L.r * L.c, R.r * R.c);
-  const double theta = fmin(1.0, fmax(fabs(L.n) * frcp(L.c), fabs(R.n) * frcp(R.c)));
+  const double ai    = K * dmax(L.r * L.c, R.r * R.c);
+  const double theta = dmin(1.0, dmax(fabs(L.n) * frcp(L.c), fabs(R.n) * frcp(R.c)));
   const double ustar = 0.5 * (R.n + L.n) - 0.5 * frcp(ai) * (R.p - L.p - 0.5 * (L.r + R.r) * gdx);
   const double Pi    = 0.5 * (R.p + L.p) - theta * 0.5 * ai * (R.n - L.n);
   const bool up      = ustar > 0.0;
@@ -667,11 +674,15 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
             qo[3] = a.kp.eps_reset;
             n_negp++;
           }
-          n_nan += (qo[0] != qo[0]) + (qo[1] != qo[1]) + (qo[2] != qo[2]) + (qo[3] != qo[3]);
-          // computeDt of the new state (ComputeDt.h:30-34)
+          // computeDt of the new state (ComputeDt.h:30-34); a NaN never wins the Max
+          // reduction (Kokkos::Max joins with `>`)
           const double cs = csound(gamma * qo[3], qo[0]);
           const double h  = (cs + fabs(qo[1])) * rdx + (cs + fabs(qo[2])) * rdy;
-          inv_dt_max      = fmax(inv_dt_max, h);
+          inv_dt_max      = (h > inv_dt_max) ? h : inv_dt_max;
+          // NaN count (SimInfo.h:624-631): h is NaN whenever a field is, so the per-field
+          // count runs only on that (rare) path
+          if (h != h)
+            n_nan += (qo[0] != qo[0]) + (qo[1] != qo[1]) + (qo[2] != qo[2]) + (qo[3] != qo[3]);
         }
 #pragma unroll
         for (int f = 0; f < 4; ++f)
