@@ -126,11 +126,15 @@ __device__ __forceinline__ double csound(double gp, double rho)
 __device__ __forceinline__ double dmax(double a, double b) { return (a > b) ? a : b; }
 __device__ __forceinline__ double dmin(double a, double b) { return (a < b) ? a : b; }
 
-// minmod (Update.h:69-85), branch-free
+// minmod (Update.h:69-85), branch-free.  "dL*dR < 0" is evaluated as "the sign bits differ"
+// on the integer pipe (one LOP3 + ISETP instead of a DMUL + DSETP on the half-rate fp64 pipe);
+// the two tests disagree only when a difference is exactly zero (the result is a zero either
+// way) or when the product underflows (|slope| < 1e-154).
 __device__ __forceinline__ double minmod_f(double dL, double dR)
 {
   const double r = (fabs(dL) < fabs(dR)) ? dL : dR;
-  return (dL * dR < 0.0) ? 0.0 : r;
+  const bool opp = (__double2hiint(dL) ^ __double2hiint(dR)) < 0;
+  return opp ? 0.0 : r;
 }
 
 // A face state in the frame of the face normal: n = normal velocity, t = tangential.
@@ -147,9 +151,20 @@ struct FaceFlux
 // HLLC (RiemannSolvers.h:53-128), re-associated: one reciprocal for 1/(rcL+rcR), one for
 // the star state of the side that is actually taken; same branch structure:
 //   SL > 0 -> left state; else uS > 0 -> left star; else SR > 0 -> right star; else right.
-__device__ __forceinline__ FaceFlux hllc_f(const FaceState &L, const FaceState &R, double entho)
+//   With FACEC == false the face states carry no sound speed: only max(cL, cR) enters the
+//   wave speeds (RiemannSolvers.h:76-77) and cL > cR <=> pL rhoR > pR rhoL, so ONE square root
+//   per face (of the faster side) replaces one per face state.
+template <bool FACEC>
+__device__ __forceinline__ FaceFlux hllc_f(const FaceState &L, const FaceState &R, double entho, double gamma)
 {
-  const double cmax = dmax(L.c, R.c);
+  double cmax;
+  if constexpr (FACEC)
+    cmax = dmax(L.c, R.c);
+  else
+  {
+    const bool lfast = L.p * R.r > R.p * L.r;
+    cmax             = csound(gamma * (lfast ? L.p : R.p), lfast ? L.r : R.r);
+  }
   const bool lt     = L.n < R.n; // one compare serves min and max
   const double SL   = (lt ? L.n : R.n) - cmax;
   const double SR   = (lt ? R.n : L.n) + cmax;
@@ -239,20 +254,35 @@ __device__ __forceinline__ FaceFlux fslp_f(const FaceState &L, const FaceState &
   return f;
 }
 
-template <int SOLVER>
-__device__ __forceinline__ FaceFlux riemann_f(const FaceState &L, const FaceState &R, double entho, double gdx, double K)
+template <int SOLVER, bool FACEC>
+__device__ __forceinline__ FaceFlux riemann_f(const FaceState &L, const FaceState &R, double entho, double gamma,
+                                              double gdx, double K)
 {
+#ifdef FV2D_TEST_NOCOMPUTE
+  FaceFlux f;
+  f.m = L.r + R.r, f.n = L.n + R.n, f.t = L.t + R.t, f.e = L.p + R.p, f.pout = L.p;
+  return f;
+#endif
   if constexpr (SOLVER == FV2D_HLL)
     return hll_f(L, R, entho);
   else if constexpr (SOLVER == FV2D_FSLP)
     return fslp_f(L, R, entho, gdx, K);
   else
-    return hllc_f(L, R, entho);
+    return hllc_f<FACEC>(L, R, entho, gamma);
 }
 
 // --------------------------------------------------------------------------- the kernel
 
-constexpr int kNS = 8; // ring depth in rows
+#ifndef FV2D_NS
+#define FV2D_NS 8
+#endif
+#ifndef FV2D_UAHEAD
+#define FV2D_UAHEAD 3
+#endif
+#ifndef FV2D_EXTRA_SMEM
+#define FV2D_EXTRA_SMEM 0 // development knob: pads the CTA's shared memory to lower the occupancy
+#endif
+constexpr int kNS = FV2D_NS; // ring depth in rows (power of two)
 
 template <int NT>
 struct SweepSmem
@@ -264,10 +294,13 @@ struct SweepSmem
 };
 
 template <int NT, bool PLM, int SOLVER, bool GRAV, bool DIFF>
-__global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : 2))
+__global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : (NT <= 256 ? 2 : 1)))
 k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepArgs a)
 {
   constexpr int W = NT - 4;
+  // Do the face states carry their sound speed?  Not for PLM + HLLC (see hllc_f); PCM has one
+  // sound speed per cell shared by its four faces, HLL / FSLP need both sides'.
+  constexpr bool FACEC = !(PLM && SOLVER == FV2D_HLLC);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SweepSmem<NT> &S = *reinterpret_cast<SweepSmem<NT> *>(smem_raw);
 
@@ -283,6 +316,9 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
   int cy = blockIdx.y;
   if ((a.peer_lo_Qout != nullptr || a.peer_hi_Qout != nullptr) && gridDim.y > 1)
     cy = (cy == 0) ? 0 : (cy == 1 ? (int)gridDim.y - 1 : cy - 1);
+#ifdef FV2D_TEST_NOMEM
+  cy = 0;
+#endif
   const int j0    = p.jbeg + cy * a.chunk_rows;
   const int j1    = min(j0 + a.chunk_rows, p.jend); // rows [j0, j1) are updated
   const int rbase = j0 - 2;                         // first row staged
@@ -350,9 +386,13 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
     yp.t = fma(0.5, s[1], qk[1]);
     yp.n = fma(0.5, s[2], qk[2]);
     yp.p = fma(0.5, s[3], qk[3]);
-    yp.c = csound(gamma * yp.p, yp.r);
+    yp.c = FACEC ? csound(gamma * yp.p, yp.r) : 0.0;
   }
 
+  double dyl[4]; // q(k+1) - q(k): the lower y difference of row k+1's slope, carried row to row
+#pragma unroll
+  for (int f = 0; f < 4; ++f)
+    dyl[f] = qn[f] - qk[f];
   FaceFlux fy_lo;  // y-face flux below row k+... (becomes the low face of the next row)
   FaceState xm;    // -x face state of row k (own cell, left face), frame of the x normal
   double rho_k = qk[0];
@@ -362,7 +402,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
   const long long ocol = L.at(0, col, 0);
   const double *Ucol   = a.Uin + ocol;
   // U rows are pulled into L2 kUAhead rows ahead of their use (one bulk prefetch per field)
-  constexpr int kUAhead     = 3;
+  constexpr int kUAhead     = FV2D_UAHEAD;
   const int ncols_strip     = min(W, p.iend - i0) & ~1;
   const uint32_t upf_bytes  = (uint32_t)ncols_strip * (uint32_t)sizeof(double);
   const double *Ustrip      = a.Uin + L.at(0, i0, 0);
@@ -377,20 +417,26 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
   double inv_dt_max = -1.7976931348623157e308;
   unsigned n_negr = 0, n_negp = 0, n_nan = 0;
 
+  // U of the own column, straight from global memory (coalesced, read once), requested ONE ROW
+  // AHEAD of its use: the load of row k+1 is issued at the top of iteration k, so a full row of
+  // arithmetic (and the row barrier) covers the HBM latency
+  double unx[4] = {0.0, 0.0, 0.0, 0.0};
+
   // ---- march: iteration k finishes row k; k = j0-1 is the warm-up (no update)
 #pragma unroll 2
   for (int k = j0 - 1; k < j1; ++k)
   {
     const int par = k & 1;
-    // U of row k, own column, straight from global memory (coalesced, read once); issued at
-    // the top of the row so its latency hides behind the row's arithmetic
     double un[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+      un[f] = unx[f];
     {
-      const int pred      = interior && (k >= j0);
-      const double *urow  = Ucol + (long long)k * L.pitch;
+      const int pred      = interior && (k + 1 < j1);
+      const double *urow  = Ucol + (long long)(k + 1) * L.pitch;
 #pragma unroll
       for (int f = 0; f < 4; ++f)
-        un[f] = ldg_stream(urow + f * L.plane, pred);
+        unx[f] = ldg_stream(urow + f * L.plane, pred);
     }
     // A. new row k+2 enters; y slopes / face states of row k+1; y-face flux at k+1/2
     wait_row(k + 2);
@@ -406,7 +452,11 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
       {
 #pragma unroll
         for (int f = 0; f < 4; ++f)
-          s[f] = minmod_f(qn[f] - qk[f], qnn[f] - qn[f]);
+        {
+          const double dup = qnn[f] - qn[f]; // also the lower difference of the next row
+          s[f]             = minmod_f(dyl[f], dup);
+          dyl[f]           = dup;
+        }
       }
       ym.r  = fma(-0.5, s[0], qn[0]);
       ym.t  = fma(-0.5, s[1], qn[1]);
@@ -416,7 +466,9 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
       yp1.t = fma(0.5, s[1], qn[1]);
       yp1.n = fma(0.5, s[2], qn[2]);
       yp1.p = fma(0.5, s[3], qn[3]);
-      if constexpr (PLM)
+      if constexpr (!FACEC)
+        ym.c = yp1.c = 0.0;
+      else if constexpr (PLM)
       {
         ym.c  = csound(gamma * ym.p, ym.r);
         yp1.c = csound(gamma * yp1.p, yp1.r);
@@ -428,7 +480,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
       }
     }
     const double gdy = p.gy * p.dy, gdx = p.gx * p.dx;
-    FaceFlux fy_hi = riemann_f<SOLVER>(yp, ym, entho, gdy, p.fslp_K);
+    FaceFlux fy_hi = riemann_f<SOLVER, FACEC>(yp, ym, entho, gamma, gdy, p.fslp_K);
 
     // B. x-face flux at the left face of (col, k): left state from the neighbour thread
     //    (also runs, on don't-care data, in the warm-up iteration: no branch, so the x and y
@@ -439,8 +491,8 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
       xl.n = S.X1[par][1][tl];
       xl.t = S.X1[par][2][tl];
       xl.p = S.X1[par][3][tl];
-      xl.c = S.X1[par][4][tl];
-      FaceFlux fx = riemann_f<SOLVER>(xl, xm, entho, gdx, p.fslp_K);
+      xl.c = FACEC ? S.X1[par][4][tl] : 0.0;
+      FaceFlux fx = riemann_f<SOLVER, FACEC>(xl, xm, entho, gamma, gdx, p.fslp_K);
       S.X2[par][0][t] = fx.m;
       S.X2[par][1][t] = fx.n;
       S.X2[par][2][t] = fx.t;
@@ -467,7 +519,9 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
       xp1.n = fma(0.5, s[1], qn[1]);
       xp1.t = fma(0.5, s[2], qn[2]);
       xp1.p = fma(0.5, s[3], qn[3]);
-      if constexpr (PLM)
+      if constexpr (!FACEC)
+        xm1.c = xp1.c = 0.0;
+      else if constexpr (PLM)
       {
         xm1.c = csound(gamma * xm1.p, xm1.r);
         xp1.c = csound(gamma * xp1.p, xp1.r);
@@ -481,7 +535,8 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
       S.X1[par ^ 1][1][t] = xp1.n;
       S.X1[par ^ 1][2][t] = xp1.t;
       S.X1[par ^ 1][3][t] = xp1.p;
-      S.X1[par ^ 1][4][t] = xp1.c;
+      if constexpr (FACEC)
+        S.X1[par ^ 1][4][t] = xp1.c;
     }
 
     __syncthreads();
@@ -641,7 +696,11 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
         }
       }
 
+#ifdef FV2D_TEST_NOMEM
+      if (interior && k >= j0 && u4[0] == 1.2345e300)
+#else
       if (interior && k >= j0)
+#endif
       {
         const long long o = ocol + (long long)k * L.pitch;
         if (a.U0 != nullptr) // SSP-RK2 combine (Update.h:214-220)
@@ -909,7 +968,7 @@ template <bool PLM, int SOLVER, bool GRAV, bool DIFF>
 static cudaError_t launch_one(const CUtensorMap &tm, const SweepArgs &a, cudaStream_t s, bool configure_only)
 {
   auto kern             = k_sweep<kNT, PLM, SOLVER, GRAV, DIFF>;
-  constexpr size_t smem = sizeof(SweepSmem<kNT>);
+  constexpr size_t smem = sizeof(SweepSmem<kNT>) + FV2D_EXTRA_SMEM;
   if (configure_only)
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int W       = kNT - 4;
