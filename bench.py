@@ -262,23 +262,31 @@ def native_arm(args):
 
     # ---- end to end through the host-buffer C ABI call: every step uploads the state from
     #      pinned host memory, advances one step and reads the new state + dt back
+    #      (N > 1: every rank does so for its own y-slab, ghost rows included; wall clock between
+    #      two barriers, maximum over the ranks)
     e2e = None
-    if world == 1 and args.e2e_steps > 0:
+    if args.e2e_steps > 0:
         hin = torch.from_numpy(Qloc).pin_memory()
         hout = torch.empty_like(hin).pin_memory()
         a_in, a_out = hin.numpy(), hout.numpy()
         dts = np.zeros(1)
         ctx.advance_host(a_in, a_out, 1, dts)  # warm-up
+        a_in, a_out = a_out, a_in
+        barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             ctx.advance_host(a_in, a_out, 1, dts)
             a_in, a_out = a_out, a_in
-        torch.cuda.synchronize()
+        barrier()
         secs = time.perf_counter() - t0
-        nbytes = int(Qloc.nbytes)
+        if world > 1:
+            tsec = torch.tensor([secs], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
+            secs = float(tsec.item())
+        nbytes = int(Qloc.nbytes) * world
         e2e = {"value": Nx * Ny * args.e2e_steps / secs / 1e6, "unit": "Mcell-updates/s",
-               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 8, "steps": args.e2e_steps,
-               "api": "fv2d_advance_host(ctx, hostQ_in, hostQ_out, 1, &dt)"}
+               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 8 * world, "steps": args.e2e_steps,
+               "api": "fv2d_advance_host(ctx, hostQ_in, hostQ_out, 1, &dt)" + (" on every rank's y-slab" if world > 1 else "")}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference itself on a bounded sample
     cpu = None

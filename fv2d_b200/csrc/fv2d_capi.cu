@@ -1032,6 +1032,19 @@ int fv2d_advance_host(fv2d_ctx *c, const double *hostQ_in, double *hostQ_out, in
   for (int64_t k = 0; k < nsteps; ++k)
     if ((rc = fused_step(c, true, 0.0)))
       return rc;
+  if (c->nranks > 1 && nsteps > 0)
+  {
+    // y-slab: the ghost rows of the new state are pushed by the neighbours' sweeps; wait for
+    // them (and fill the x ghosts) so the array handed back is complete and can be fed to the
+    // next call as it is
+    StepBeginArgs b;
+    std::memset(&b, 0, sizeof b);
+    const unsigned long long pushes_per_sweep =
+        2ULL * ((c->kp.p.Nx + sweep_strip_width() - 1) / sweep_strip_width());
+    b.halo_expected = c->halo_gen * pushes_per_sweep;
+    launch_step_begin(c->kp, c->Q[c->cur], b, c->stream);
+    c->n_launch_total++;
+  }
   if ((rc = copy_d2h(c, hostQ_out, c->Q[c->cur])))
     return rc;
   if (dts)

@@ -279,6 +279,9 @@ __device__ __forceinline__ FaceFlux riemann_f(const FaceState &L, const FaceStat
 #ifndef FV2D_UAHEAD
 #define FV2D_UAHEAD 3
 #endif
+#ifndef FV2D_MINBLOCKS
+#define FV2D_MINBLOCKS(NT) ((NT) <= 128 ? 4 : ((NT) <= 256 ? 2 : 1))
+#endif
 #ifndef FV2D_EXTRA_SMEM
 #define FV2D_EXTRA_SMEM 0 // development knob: pads the CTA's shared memory to lower the occupancy
 #endif

@@ -92,3 +92,61 @@ def test_n_gpu_result_is_bitwise_the_1_gpu_result(name, ov, nranks):
     I = slice(dev.ibeg, dev.iend)
     assert np.array_equal(Un[:, J, I], U1[:, J, I])
     assert np.array_equal(Qn[:, J, I], Q1[:, J, I])
+
+
+def test_advance_host_on_slabs_round_trips_complete_arrays():
+    """fv2d_advance_host on y-slabs: the array handed back (ghost rows included, they are pushed
+    by the neighbour) fed to the next call must reproduce, bitwise, the same host round trip on
+    one GPU (each call rebuilds U from the primitive state, like a restart: main.cpp:58)."""
+    import threading
+
+    nranks = 2
+    if _ngpu() < nranks:
+        pytest.skip("needs 2 GPUs")
+    dev, run = capi.params_from_ini(load_golden("kh_plm_128x64").ini_path(), {"mesh.Nx": 300, "mesh.Ny": 128})
+    Q0 = capi.init_problem(dev, run)
+    n = 4
+    with capi.Context(dev, run.time_stepping, run.epsilon_reset_negative) as ctx:
+        a, b, d1 = Q0.copy(), np.empty_like(Q0), np.zeros(1)
+        hist = []
+        for _ in range(n):
+            ctx.advance_host(a, b, 1, d1)
+            hist.append(d1[0])
+            a, b = b, a
+        Q1, dts1 = a, np.array(hist)
+    ctxs = [capi.Context(dev, run.time_stepping, run.epsilon_reset_negative, device=r, rank=r, nranks=nranks)
+            for r in range(nranks)]
+    try:
+        multigpu.connect_local(ctxs)
+        outs, errs = [None] * nranks, []
+
+        def work(r):
+            try:
+                a = np.ascontiguousarray(multigpu.split_global(Q0, dev.Ng, r, nranks))
+                b = np.empty_like(a)
+                dts = np.zeros(1)
+                hist = []
+                for _ in range(n):
+                    ctxs[r].advance_host(a, b, 1, dts)
+                    hist.append(dts[0])
+                    a, b = b, a
+                outs[r] = (a, np.array(hist))
+            except Exception as e:  # noqa
+                errs.append(e)
+
+        th = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert not errs, errs
+        Qn = multigpu.join_slabs([o[0] for o in outs], dev.Ng)
+        J, I = slice(dev.jbeg, dev.jend), slice(dev.ibeg, dev.iend)
+        assert np.array_equal(Qn[:, J, I], Q1[:, J, I])
+        for o in outs:
+            assert np.array_equal(o[1], dts1)
+    finally:
+        for c in ctxs:
+            c.sync()
+        for c in ctxs:
+            c.close()
