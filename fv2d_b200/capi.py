@@ -150,6 +150,10 @@ def lib() -> C.CDLL:
         "fv2d_params_dump_ini": [C.c_char_p, C.c_char_p, C.c_char_p],
         "fv2d_init_problem": [C.POINTER(DeviceParams), C.POINTER(RunParams), _dp],
         "fv2d_init_problem_rows": [C.POINTER(DeviceParams), C.POINTER(RunParams), C.c_int, C.c_int, _dp],
+        "fv2d_io_save_solution": [C.POINTER(DeviceParams), C.POINTER(RunParams), _dp, C.c_int, C.c_double,
+                                  C.POINTER(C.c_int)],
+        "fv2d_io_load_snapshot": [C.POINTER(DeviceParams), C.POINTER(RunParams), _dp, _dp, C.POINTER(C.c_int),
+                                  C.POINTER(C.c_int)],
         "fv2d_ctx_create": [C.POINTER(DeviceParams), C.c_int, C.c_double, C.c_int, C.POINTER(_ctxp)],
         "fv2d_ctx_create_slab": [C.POINTER(DeviceParams), C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(_ctxp)],
         "fv2d_ctx_set_stream": [_ctxp, C.c_void_p],
@@ -238,6 +242,25 @@ def init_problem_rows(dev: DeviceParams, run: RunParams, j_first: int, nrows: in
     Q = np.zeros((4, nrows, dev.Ntx), dtype=np.float64)
     _check(lib().fv2d_init_problem_rows(C.byref(dev), C.byref(run), j_first, nrows, _ptr(Q)))
     return Q
+
+
+def io_save_solution(dev: DeviceParams, run: RunParams, Q: np.ndarray, iteration: int, t: float,
+                     force_file_truncation: bool = False) -> bool:
+    """IOManager::saveSolution on a host array (IOManager.h:99-282); returns the updated
+    force_file_truncation flag."""
+    assert Q.shape == dev.shape()
+    flag = C.c_int(1 if force_file_truncation else 0)
+    _check(lib().fv2d_io_save_solution(C.byref(dev), C.byref(run), _ptr(Q), iteration, t, C.byref(flag)))
+    return bool(flag.value)
+
+
+def io_load_snapshot(dev: DeviceParams, run: RunParams, force_file_truncation: bool = False):
+    """IOManager::loadSnapshot (IOManager.h:284-398) -> (Q with ghosts, time, iteration,
+    force_file_truncation)."""
+    Q = np.zeros(dev.shape(), dtype=np.float64)
+    t, it, flag = C.c_double(0.0), C.c_int(0), C.c_int(1 if force_file_truncation else 0)
+    _check(lib().fv2d_io_load_snapshot(C.byref(dev), C.byref(run), _ptr(Q), C.byref(t), C.byref(it), C.byref(flag)))
+    return Q, t.value, it.value, bool(flag.value)
 
 
 class Context:

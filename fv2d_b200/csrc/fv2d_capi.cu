@@ -11,6 +11,7 @@
 
 #include "../host/Init.h"
 #include "../host/SimInfo.h"
+#include "../host/SnapshotIO.h"
 #include "fv2d_kernels.h"
 
 namespace fv2d
@@ -459,6 +460,63 @@ int fv2d_init_problem_rows(const fv2d_device_params *dev, const fv2d_run_params 
   {
     set_error(e.what());
     return FV2D_ERR_CONFIG;
+  }
+  return FV2D_OK;
+}
+
+static SnapshotConfig snapshot_config(const fv2d_device_params *dev, const fv2d_run_params *run)
+{
+  SnapshotConfig c;
+  c.device_params    = *dev;
+  c.output_path      = run->output_path;
+  c.filename_out     = run->filename_out;
+  c.restart_file     = run->restart_file;
+  c.problem          = run->problem;
+  c.multiple_outputs = run->multiple_outputs != 0;
+  c.tend             = run->tend;
+  return c;
+}
+
+int fv2d_io_save_solution(const fv2d_device_params *dev, const fv2d_run_params *run, const double *hostQ,
+                          int iteration, double t, int *force_file_truncation)
+{
+  if (!dev || !run || !hostQ || !force_file_truncation)
+    return arg_fail("null argument");
+  try
+  {
+    HostArray Q(dev->Nty, dev->Ntx);
+    std::memcpy(Q.data.data(), hostQ, Q.data.size() * sizeof(double));
+    bool force = *force_file_truncation != 0;
+    saveSolutionHost(snapshot_config(dev, run), Q, iteration, t, force);
+    *force_file_truncation = force ? 1 : 0;
+  }
+  catch (const std::exception &e)
+  {
+    set_error(e.what());
+    return FV2D_ERR_IO;
+  }
+  return FV2D_OK;
+}
+
+int fv2d_io_load_snapshot(const fv2d_device_params *dev, const fv2d_run_params *run, double *hostQ, double *time,
+                          int *iteration, int *force_file_truncation)
+{
+  if (!dev || !run || !hostQ || !time || !iteration || !force_file_truncation)
+    return arg_fail("null argument");
+  try
+  {
+    HostArray Q(dev->Nty, dev->Ntx);
+    bool force             = *force_file_truncation != 0;
+    const RestartInfo info = loadSnapshotHost(snapshot_config(dev, run), Q, force);
+    std::memcpy(hostQ, Q.data.data(), Q.data.size() * sizeof(double));
+    *time                  = info.time;
+    *iteration             = info.iteration;
+    *force_file_truncation = force ? 1 : 0;
+  }
+  catch (const std::exception &e)
+  {
+    set_error(e.what());
+    return FV2D_ERR_IO;
   }
   return FV2D_OK;
 }

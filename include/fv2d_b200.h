@@ -67,6 +67,25 @@ int fv2d_init_problem(const fv2d_device_params *dev, const fv2d_run_params *run,
 int fv2d_init_problem_rows(const fv2d_device_params *dev, const fv2d_run_params *run, int j_first, int nrows,
                            double *hostQ_rows);
 
+/* replaces IOManager::saveSolution(Q, iteration, t) on a host copy of Q
+ *                                                                   (IOManager.h:99-282)
+ * Writes <output_path>/<filename_out>.h5 (+ .xmf): root attributes, vertex datasets x / y and
+ * one group ite_%04d per snapshot (or, with run->multiple_outputs, one .h5/.xmf pair per
+ * snapshot).  HDF5 is written by the library's own dependency-free writer.
+ * *force_file_truncation is the IOManager member of the same name (IOManager.h:80), in/out:
+ * the file is truncated when it is non-zero or iteration == 0, appended to otherwise. */
+int fv2d_io_save_solution(const fv2d_device_params *dev, const fv2d_run_params *run, const double *hostQ,
+                          int iteration, double t, int *force_file_truncation);
+
+/* replaces IOManager::loadSnapshot(Q)                                (IOManager.h:284-398)
+ * Reads run->restart_file ("file.h5" = last iteration, "file.h5:/ite_0005" = that group, or a
+ * multiple-outputs snapshot file) into hostQ (zero-filled first), fills the ghost cells
+ * (IOManager.h:378-379) and refuses to restart past run->tend (:381-387).  When
+ * *force_file_truncation comes back non-zero the caller must re-save the loaded state
+ * (IOManager.h:391-395), as the C++ IOManager does. */
+int fv2d_io_load_snapshot(const fv2d_device_params *dev, const fv2d_run_params *run, double *hostQ, double *time,
+                          int *iteration, int *force_file_truncation);
+
 /* ------------------------------------------------------------------ context */
 
 /* Allocates Q and U (zero-filled, like Kokkos Views: main.cpp:33-34) on CUDA device

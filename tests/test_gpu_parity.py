@@ -228,15 +228,52 @@ def test_cpp_host_driver_runs_the_reference_loop(tmp_path):
         assert r.returncode == 0, r.stderr
         assert "Computing dts at (t=0) : dt_hyp=0.00968246" in r.stdout
         outs[bool(mode)] = r.stdout
-        snaps = sorted(tmp_path.glob("run_*.bin"))
-        assert snaps, "no snapshot written"
-        raw = snaps[-1].read_bytes()
-        assert raw[:8] == b"FV2DSNAP"
-        nx, ny, ite, _ = np.frombuffer(raw, "<i4", 4, 8)
-        t = float(np.frombuffer(raw, "<f8", 1, 24)[0])
-        rho = np.frombuffer(raw, "<f8", nx * ny, 32).reshape(ny, nx)
-        assert (nx, ny) == (64, 16) and abs(t - g.t) <= 1e-13 * g.t
+        import h5mini
+
+        f = h5mini.File(tmp_path / "run.h5")
+        groups = [k for k in f.keys() if k.startswith("ite_")]
+        assert groups == ["ite_0000", "ite_0001"] and f.keys()[-2:] == ["x", "y"]
+        assert int(f.attrs["Nx"]) == 64 and int(f.attrs["Ny"]) == 16 and f.attrs["problem"] == "sod_x"
+        last = f["ite_0001"]
+        t = float(last.attrs["time"])
+        assert abs(t - g.t) <= 1e-13 * g.t and int(last.attrs["iteration"]) == 1
+        rho = last["rho"].read().reshape(16, 64)
         assert rel_l1(rho, g.QN[0]) <= TOL_L1
-        for s in snaps:
-            s.unlink()
+        assert np.array_equal(f["ite_0000/rho"].read().reshape(16, 64), g.Q0[0])
+        assert "ite_0001/prs" in (tmp_path / "run.xmf").read_text()
+        (tmp_path / "run.h5").unlink()
     assert (tmp_path / "last.ini").read_text().startswith("; Parameters used for the problem: sod_x")
+
+
+def test_cpp_host_driver_restart_from_run_h5(tmp_path):
+    """Restart (main.cpp:47-55, IOManager.h:284-398): 10 steps, snapshot, restart for 10 more ==
+    20 steps in one go (the restart file stores Q only; U is recomputed, main.cpp:58)."""
+    import h5mini
+
+    exe = ROOT / "fv2d_b200" / "fv2d_b200_main"
+    if not exe.exists():
+        subprocess.run(["make", "driver"], cwd=ROOT, check=True, capture_output=True)
+    g = load_golden("sod_x")
+    ini = Path(g.ini_path()).read_text().replace("save_freq=0.01", "save_freq=1.0")  # no intermediate snapshot
+    assert "save_freq=1.0" in ini
+    a, b = tmp_path / "a", tmp_path / "b"
+    a.mkdir(), b.mkdir()
+    ini1 = tmp_path / "sod.ini"
+    ini1.write_text(ini)
+    r = subprocess.run([str(exe), str(ini1), "--max-steps", "20", "--quiet"], cwd=a, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), str(ini1), "--max-steps", "10", "--quiet"], cwd=b, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    (b / "first.h5").write_bytes((b / "run.h5").read_bytes())
+    ini2 = b / "restart.ini"
+    ini2.write_text(ini.replace("[run]", "[run]\nrestart_file=first.h5"))
+    r = subprocess.run([str(exe), str(ini2), "--max-steps", "10", "--quiet"], cwd=b, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Restart at iteration 1" in r.stdout
+    fa, fb = h5mini.File(a / "run.h5"), h5mini.File(b / "run.h5")
+    # restarted run: truncated file re-saved the loaded state as ite_0001, then wrote ite_0002 at the end
+    assert [k for k in fb.keys() if k.startswith("ite_")] == ["ite_0001", "ite_0002"]
+    ta, tb = float(fa["ite_0001"].attrs["time"]), float(fb["ite_0002"].attrs["time"])
+    assert abs(ta - tb) <= 1e-13 * ta
+    for fld in ("rho", "u", "v", "prs"):
+        assert rel_l1(fb["ite_0002/" + fld].read(), fa["ite_0001/" + fld].read()) <= TOL_L1
