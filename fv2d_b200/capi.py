@@ -189,6 +189,7 @@ def lib() -> C.CDLL:
         "fv2d_halo_export": [_ctxp, C.c_void_p],
         "fv2d_halo_connect": [_ctxp, C.c_char_p, C.c_int],
         "fv2d_get_inv_dt": [_ctxp, _dp],
+        "fv2d_debug_math_probe": [C.c_int, C.c_int64, _dp, _dp, _dp, _dp],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)
@@ -261,6 +262,16 @@ def io_load_snapshot(dev: DeviceParams, run: RunParams, force_file_truncation: b
     t, it, flag = C.c_double(0.0), C.c_int(0), C.c_int(1 if force_file_truncation else 0)
     _check(lib().fv2d_io_load_snapshot(C.byref(dev), C.byref(run), _ptr(Q), C.byref(t), C.byref(it), C.byref(flag)))
     return Q, t.value, it.value, bool(flag.value)
+
+
+def math_probe(a: np.ndarray, b: np.ndarray, device: int = 0):
+    """(1/a, sqrt(a/b)) as the fused sweep's division-free primitives compute them."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    assert a.shape == b.shape and a.ndim == 1
+    r, c = np.empty_like(a), np.empty_like(a)
+    _check(lib().fv2d_debug_math_probe(device, a.size, _ptr(a), _ptr(b), _ptr(r), _ptr(c)))
+    return r, c
 
 
 class Context:

@@ -1038,6 +1038,31 @@ int fv2d_integrate_mass_energy(fv2d_ctx *c, double *mass, double *energy)
   return FV2D_OK;
 }
 
+int fv2d_debug_math_probe(int device, int64_t n, const double *a, const double *b, double *out_rcp, double *out_cs)
+{
+  if (n <= 0 || !a || !b || !out_rcp || !out_cs)
+    return arg_fail("fv2d_debug_math_probe: bad arguments");
+  FV2D_CUDA(cudaSetDevice(device));
+  double *d           = nullptr;
+  const size_t nbytes = (size_t)n * sizeof(double);
+  FV2D_CUDA(cudaMalloc(&d, 4 * nbytes));
+  cudaError_t e = cudaMemcpy(d, a, nbytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(d + n, b, nbytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+  {
+    launch_math_probe(n, d, d + n, d + 2 * n, d + 3 * n, nullptr);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess)
+    e = cudaMemcpy(out_rcp, d + 2 * n, nbytes, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(out_cs, d + 3 * n, nbytes, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  FV2D_CUDA(e);
+  return FV2D_OK;
+}
+
 int fv2d_profile_enable(fv2d_ctx *c, int on)
 {
   FV2D_ENTER(c);

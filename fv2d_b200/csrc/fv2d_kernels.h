@@ -62,5 +62,7 @@ cudaError_t launch_sweep(const CUtensorMap &tmapQ, const SweepArgs &a, cudaStrea
 // Opt-in dynamic shared memory etc.; call once per process before the first sweep.
 cudaError_t sweep_configure();
 int sweep_strip_width();
+// Accuracy probe of the sweep's reciprocal / sound-speed primitives (device pointers).
+void launch_math_probe(long long n, const double *a, const double *b, double *out_rcp, double *out_cs, cudaStream_t s);
 
 } // namespace fv2d

@@ -68,6 +68,18 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, 
                : "memory");
 }
 
+// Same, on precomputed shared-window addresses (keeps the producer's per-row work short)
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_u32(uint32_t dst, const CUtensorMap *tmap, int x, int y, int z, uint32_t bar)
+{
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar)
+               : "memory");
+}
+
 // Asks the L2 to fetch `bytes` (multiple of 16) starting at the 16-byte aligned `ptr`
 // (SASS: UBLKPF).  Used to pull the U rows a few rows ahead of the sweep so the later
 // per-thread loads hit in L2 instead of paying the loaded-HBM latency.
@@ -92,24 +104,50 @@ __device__ __forceinline__ double ldg_stream(const double *ptr, int pred)
   return v;
 }
 
-// 1/a: MUFU.RCP64H seed (>= 20 bits) + two Newton steps -> ~1 ulp, no slow path
+// Development knobs for the A/B variants built by scripts/build_variant.sh (defaults = shipped).
+#ifndef FV2D_FAST_RCP
+#define FV2D_FAST_RCP 1
+#endif
+#ifndef FV2D_FAST_CS
+#define FV2D_FAST_CS 1
+#endif
+#ifndef FV2D_PS_SHORT
+#define FV2D_PS_SHORT 1
+#endif
+
+// 1/a: MUFU.RCP64H seed (relative error e0 <= ~2^-18) + ONE third-order step
+//   y1 = y0 (1 + e + e^2),  e = 1 - a y0   ->  relative error e0^3 < 2^-54, i.e. ~1 ulp with
+// the rounding of the last fma; three dependent DFMAs, no IEEE slow path.  (div.rn.f64 itself
+// starts with exactly this step and then spends five more instructions on correct rounding.)
 __device__ __forceinline__ double frcp(double a)
 {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+#if FV2D_FAST_RCP
+  const double e = fma(-a, y, 1.0);
+  const double t = fma(e, e, e);
+  return fma(y, t, y);
+#else
   double e = fma(-a, y, 1.0);
   y        = fma(y, e, y);
   e        = fma(-a, y, 1.0);
   y        = fma(y, e, y);
   return y;
+#endif
 }
-// sound speed sqrt(gp / rho) with gp = gamma0 * P: c = gp * rsqrt(gp * rho);
-// MUFU.RSQ64H seed + two coupled (Goldschmidt) steps
+// sound speed sqrt(gp / rho) with gp = gamma0 * P:  c = gp * rsqrt(gp * rho).
+// MUFU.RSQ64H seed r + ONE third-order step  1/sqrt(y) = r (1 + e/2 + 3 e^2 / 8),
+// e = 1 - y r^2  (|e| <= ~2^-17 -> truncation 5 e^3 / 16 < 2^-52): 7 fp64 instructions.
 __device__ __forceinline__ double csound(double gp, double rho)
 {
   const double y = gp * rho;
   double r;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+#if FV2D_FAST_CS
+  const double e = fma(-y, r * r, 1.0);
+  const double t = fma(0.375, e, 0.5) * e;
+  return gp * fma(r, t, r);
+#else
   double g = y * r;   // ~ sqrt(y)
   double h = 0.5 * r; // ~ 1 / (2 sqrt(y))
   double e = fma(-g, h, 0.5);
@@ -118,6 +156,7 @@ __device__ __forceinline__ double csound(double gp, double rho)
   e        = fma(-g, h, 0.5);
   h        = fma(h, e, h);
   return (gp + gp) * h;
+#endif
 }
 
 // max / min as one DSETP + two FSEL.  fmax()/fmin() lower to ~8 instructions each on sm_100a
@@ -173,7 +212,13 @@ __device__ __forceinline__ FaceFlux hllc_f(const FaceState &L, const FaceState &
   const double rcR = R.r * (SR - R.n);
   const double inv = frcp(rcR + rcL);
   const double uS  = (rcR * R.n + rcL * L.n + (L.p - R.p)) * inv;
+#if FV2D_PS_SHORT
+  // p* = pL + rhoL (SL - uL)(u* - uL)  (Toro 10.36; algebraically the reference's
+  // (rcR pL + rcL pR + rcL rcR (uL - uR)) / (rcL + rcR), RiemannSolvers.h:83): 2 instructions
+  const double pS = fma(rcL, L.n - uS, L.p);
+#else
   const double pS  = (rcR * L.p + rcL * R.p + rcL * rcR * (L.n - R.n)) * inv;
+#endif
 
   const bool left = (SL > 0.0) || (uS > 0.0);
   const bool star = left ? !(SL > 0.0) : (SR > 0.0);
@@ -282,18 +327,27 @@ __device__ __forceinline__ FaceFlux riemann_f(const FaceState &L, const FaceStat
 #ifndef FV2D_MINBLOCKS
 #define FV2D_MINBLOCKS(NT) ((NT) <= 128 ? 4 : ((NT) <= 256 ? 2 : 1))
 #endif
+#ifndef FV2D_UNROLL
+#define FV2D_UNROLL 2 // rows per loop body (2 rows = 19 KB of code, inside the 32 KB L1.5 I-cache)
+#endif
 #ifndef FV2D_EXTRA_SMEM
 #define FV2D_EXTRA_SMEM 0 // development knob: pads the CTA's shared memory to lower the occupancy
 #endif
 constexpr int kNS = FV2D_NS; // ring depth in rows (power of two)
+constexpr int kUnroll = FV2D_UNROLL;
 
 template <int NT>
 struct SweepSmem
 {
   double ring[kNS][4][NT]; // TMA destination: [slot][field][column]
-  double X1[2][5][NT];     // +x face state (r,u,v,p,c) of each column, by row parity
-  double X2[2][4][NT];     // x-face flux (m,n,t,e) at the LEFT face of each column, by row parity
-  uint64_t full[kNS];      // TMA completion barriers
+  // exchange arrays, by row parity; fields are paired so that every access is one conflict-free
+  // 128-bit LDS / STS (16-byte stride between neighbouring threads)
+  double2 X1a[2][NT]; // +x face state of each column: (r, n)
+  double2 X1b[2][NT]; //                                (t, p)
+  double X1c[2][NT];  //                                 c   (only when face states carry it)
+  double2 X2a[2][NT]; // x-face flux at the LEFT face of each column: (m, n)
+  double2 X2b[2][NT]; //                                              (t, e)
+  uint64_t full[kNS]; // TMA completion barriers
 };
 
 template <int NT, bool PLM, int SOLVER, bool GRAV, bool DIFF>
@@ -403,19 +457,34 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
   xm.r = xm.n = xm.t = xm.p = xm.c = 0.0;
 
   const long long ocol = L.at(0, col, 0);
-  const double *Ucol   = a.Uin + ocol;
+  // Global addresses = uniform per-(array, field) base + one per-thread byte offset that is
+  // carried and bumped by a row pitch per iteration (two integer instructions per address).
+  const long long pitchB = (long long)L.pitch * (long long)sizeof(double);
+  const long long planeB = L.plane * (long long)sizeof(double);
+  long long offB         = (ocol + (long long)(j0 - 1) * L.pitch) * (long long)sizeof(double); // row k
+  const char *const UinB  = reinterpret_cast<const char *>(a.Uin);
+  char *const UoutB       = reinterpret_cast<char *>(a.Uout);
+  char *const QoutB       = reinterpret_cast<char *>(a.Qout);
   // U rows are pulled into L2 kUAhead rows ahead of their use (one bulk prefetch per field)
   constexpr int kUAhead     = FV2D_UAHEAD;
   const int ncols_strip     = min(W, p.iend - i0) & ~1;
   const uint32_t upf_bytes  = (uint32_t)ncols_strip * (uint32_t)sizeof(double);
   const double *Ustrip      = a.Uin + L.at(0, i0, 0);
-  if (t == 0 && upf_bytes > 0)
+  // the prefetching thread sits in another warp than the TMA producer (t == 0), so that no
+  // single warp carries all the per-row bookkeeping into the row barrier
+  constexpr int kPfThread = (NT > 32) ? 32 : 0;
+  const bool pf_thread    = (kUAhead > 0) && (t == kPfThread) && (upf_bytes > 0);
+  const char *pf_ptr      = reinterpret_cast<const char *>(Ustrip + (long long)(j0 + kUAhead) * L.pitch); // row k+1+kUAhead
+  if (pf_thread)
   {
     for (int r = j0; r < min(j0 + kUAhead, j1); ++r)
 #pragma unroll
       for (int f = 0; f < 4; ++f)
         l2_prefetch(Ustrip + f * L.plane + (long long)r * L.pitch, upf_bytes);
   }
+  const uint32_t ring0 = smem_u32(&S.ring[0][0][0]);
+  const uint32_t bar0  = smem_u32(&S.full[0]);
+  const int k_refill_last = rlast - kNS + 2; // last iteration that still has a row to stage
 
   double inv_dt_max = -1.7976931348623157e308;
   unsigned n_negr = 0, n_negp = 0, n_nan = 0;
@@ -426,7 +495,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
   double unx[4] = {0.0, 0.0, 0.0, 0.0};
 
   // ---- march: iteration k finishes row k; k = j0-1 is the warm-up (no update)
-#pragma unroll 2
+#pragma unroll kUnroll
   for (int k = j0 - 1; k < j1; ++k)
   {
     const int par = k & 1;
@@ -435,11 +504,10 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
     for (int f = 0; f < 4; ++f)
       un[f] = unx[f];
     {
-      const int pred      = interior && (k + 1 < j1);
-      const double *urow  = Ucol + (long long)(k + 1) * L.pitch;
+      const int pred = interior && (k + 1 < j1);
 #pragma unroll
       for (int f = 0; f < 4; ++f)
-        unx[f] = ldg_stream(urow + f * L.plane, pred);
+        unx[f] = ldg_stream(reinterpret_cast<const double *>(UinB + f * planeB + (offB + pitchB)), pred);
     }
     // A. new row k+2 enters; y slopes / face states of row k+1; y-face flux at k+1/2
     wait_row(k + 2);
@@ -490,16 +558,12 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
     //    Riemann problems of a row can be scheduled together)
     {
       FaceState xl;
-      xl.r = S.X1[par][0][tl];
-      xl.n = S.X1[par][1][tl];
-      xl.t = S.X1[par][2][tl];
-      xl.p = S.X1[par][3][tl];
-      xl.c = FACEC ? S.X1[par][4][tl] : 0.0;
+      const double2 la = S.X1a[par][tl], lb = S.X1b[par][tl];
+      xl.r = la.x, xl.n = la.y, xl.t = lb.x, xl.p = lb.y;
+      xl.c = FACEC ? S.X1c[par][tl] : 0.0;
       FaceFlux fx = riemann_f<SOLVER, FACEC>(xl, xm, entho, gamma, gdx, p.fslp_K);
-      S.X2[par][0][t] = fx.m;
-      S.X2[par][1][t] = fx.n;
-      S.X2[par][2][t] = fx.t;
-      S.X2[par][3][t] = fx.e;
+      S.X2a[par][t] = make_double2(fx.m, fx.n);
+      S.X2b[par][t] = make_double2(fx.t, fx.e);
     }
 
     // C. x slopes / face states of row k+1 (published for the neighbour on the right)
@@ -534,47 +598,41 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
         xm1.c = ym.c; // PCM: one sound speed per cell
         xp1.c = ym.c;
       }
-      S.X1[par ^ 1][0][t] = xp1.r;
-      S.X1[par ^ 1][1][t] = xp1.n;
-      S.X1[par ^ 1][2][t] = xp1.t;
-      S.X1[par ^ 1][3][t] = xp1.p;
+      S.X1a[par ^ 1][t] = make_double2(xp1.r, xp1.n);
+      S.X1b[par ^ 1][t] = make_double2(xp1.t, xp1.p);
       if constexpr (FACEC)
-        S.X1[par ^ 1][4][t] = xp1.c;
+        S.X1c[par ^ 1][t] = xp1.c;
     }
 
     __syncthreads();
 
     // E. refill the ring slot of row k-2 (no thread reads it any more) with row k-2+NS
-    if (t == 0)
+    if (t == 0 && k >= j0 && k <= k_refill_last)
     {
-      const int rnew = k - 2 + kNS;
-      if (k - 2 >= rbase && rnew <= rlast)
-      {
-        const int s = slot_of(rnew);
-        mbar_expect_tx(&S.full[s], kRowBytes);
-        tma_load_3d(&S.ring[s][0][0], &tmQ, tma_x, rnew, 0, &S.full[s]);
-      }
-      const int rpf = k + 1 + kUAhead;
-      if (rpf < j1 && upf_bytes > 0)
+      const uint32_t s = (uint32_t)slot_of(k - 2);
+      mbar_expect_tx_u32(bar0 + 8u * s, kRowBytes);
+      tma_load_3d_u32(ring0 + kRowBytes * s, &tmQ, tma_x, k - 2 + kNS, 0, bar0 + 8u * s);
+    }
+    if constexpr (kUAhead > 0)
+    {
+      if (pf_thread && k + 1 + kUAhead < j1)
       {
 #pragma unroll
         for (int f = 0; f < 4; ++f)
-          l2_prefetch(Ustrip + f * L.plane + (long long)rpf * L.pitch, upf_bytes);
+          l2_prefetch(pf_ptr + f * planeB, upf_bytes);
       }
+      pf_ptr += pitchB;
     }
 
     // D. finish row k
     {
-      FaceFlux fxr;
-      fxr.m = S.X2[par][0][tr];
-      fxr.n = S.X2[par][1][tr];
-      fxr.t = S.X2[par][2][tr];
-      fxr.e = S.X2[par][3][tr];
-      FaceFlux fxl;
-      fxl.m = S.X2[par][0][t];
-      fxl.n = S.X2[par][1][t];
-      fxl.t = S.X2[par][2][t];
-      fxl.e = S.X2[par][3][t];
+      FaceFlux fxr, fxl;
+      {
+        const double2 ra = S.X2a[par][tr], rb = S.X2b[par][tr];
+        const double2 oa = S.X2a[par][t], ob = S.X2b[par][t];
+        fxr.m = ra.x, fxr.n = ra.y, fxr.t = rb.x, fxr.e = rb.y;
+        fxl.m = oa.x, fxl.n = oa.y, fxl.t = ob.x, fxl.e = ob.y;
+      }
 
       // y fluxes back in the grid frame: (m, t, n, e) -> (rho, rho u, rho v, E)
       double fyl[4] = {fy_lo.m, fy_lo.t, fy_lo.n, fy_lo.e};
@@ -705,16 +763,16 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
       if (interior && k >= j0)
 #endif
       {
-        const long long o = ocol + (long long)k * L.pitch;
         if (a.U0 != nullptr) // SSP-RK2 combine (Update.h:214-220)
         {
+          const char *U0B = reinterpret_cast<const char *>(a.U0);
 #pragma unroll
           for (int f = 0; f < 4; ++f)
-            u4[f] = 0.5 * (a.U0[o + f * L.plane] + u4[f]);
+            u4[f] = 0.5 * (*reinterpret_cast<const double *>(U0B + f * planeB + offB) + u4[f]);
         }
 #pragma unroll
         for (int f = 0; f < 4; ++f)
-          a.Uout[o + f * L.plane] = u4[f];
+          *reinterpret_cast<double *>(UoutB + f * planeB + offB) = u4[f];
 
         // consToPrim (States.h:32-43)
         const double ir = frcp(u4[0]);
@@ -748,7 +806,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
         }
 #pragma unroll
         for (int f = 0; f < 4; ++f)
-          a.Qout[o + f * L.plane] = qo[f];
+          *reinterpret_cast<double *>(QoutB + f * planeB + offB) = qo[f];
         // multi-GPU: the slab's two edge rows are also the neighbour's ghost rows — store them
         // straight into the neighbour's memory (peer mapping over NVLink)
         if (a.peer_lo_Qout != nullptr && k < p.jbeg + 2)
@@ -769,6 +827,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
     }
 
     // roll the column window
+    offB += pitchB;
     fy_lo = fy_hi;
     yp    = yp1;
     xm    = xm1;
@@ -811,8 +870,8 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
       n_negp += __shfl_xor_sync(0xffffffffu, n_negp, o);
       n_nan += __shfl_xor_sync(0xffffffffu, n_nan, o);
     }
-    __syncthreads(); // X2 is free now: reuse as scratch
-    double *red = &S.X2[0][0][0];
+    __syncthreads(); // X2a is free now: reuse as scratch
+    double *red = reinterpret_cast<double *>(&S.X2a[0][0]);
     if ((t & 31) == 0)
       red[t >> 5] = inv_dt_max;
     if ((t & 31) == 0)
@@ -844,6 +903,26 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
       }
     }
   }
+}
+
+// --------------------------------------------------------------------------- math probe
+
+// Evaluates the sweep's division-free primitives on arbitrary inputs so that their accuracy is a
+// tested property (tests/test_gpu_properties.py): out_rcp[i] = frcp(a[i]),
+// out_cs[i] = csound(a[i], b[i]) = sqrt(a[i] / b[i]).
+__global__ void k_math_probe(long long n, const double *__restrict__ a, const double *__restrict__ b,
+                             double *__restrict__ out_rcp, double *__restrict__ out_cs)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+  {
+    out_rcp[i] = frcp(a[i]);
+    out_cs[i]  = csound(a[i], b[i]);
+  }
+}
+void launch_math_probe(long long n, const double *a, const double *b, double *out_rcp, double *out_cs, cudaStream_t s)
+{
+  k_math_probe<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, a, b, out_rcp, out_cs);
 }
 
 // --------------------------------------------------------------------------- step prologue

@@ -183,6 +183,12 @@ int fv2d_integrate_mass_energy(fv2d_ctx *ctx, double *mass, double *energy);
 int fv2d_profile_enable(fv2d_ctx *ctx, int on);
 int fv2d_profile_read(fv2d_ctx *ctx, double *sweep_ms, int64_t *sweep_launches, int64_t *total_launches);
 
+/* Test hook: the fused kernel replaces IEEE division / sqrt by MUFU seeds + one third-order
+ * correction step.  Evaluates those primitives on host arrays of length n on CUDA device
+ * `device`: out_rcp[i] = 1 / a[i], out_cs[i] = sqrt(a[i] / b[i]) as the sweep computes them
+ * (States.h:46 speedOfSound with a = gamma0 * P, b = rho). */
+int fv2d_debug_math_probe(int device, int64_t n, const double *a, const double *b, double *out_rcp, double *out_cs);
+
 /* Host-buffer convenience used for end-to-end measurement: upload Q (pinned or pageable
  * host memory), primToCons, computeDt, run `nsteps` fused steps, download Q; dts (may be
  * NULL) receives the dt sequence.  Equivalent to the reference main.cpp:58-84 on a state

@@ -111,3 +111,23 @@ def test_sod_x_y_symmetry_on_device():
     assert np.max(np.abs(res[0][1] - res[1][1]) / res[0][1]) <= 1e-13
     assert rel_l1(res[0][0][0], res[1][0][0].T) <= 1e-12
     assert rel_l1(res[0][0][3], res[1][0][3].T) <= 1e-12
+
+
+def test_division_free_primitives_are_accurate_to_a_few_ulp():
+    """The sweep computes 1/x and sqrt(gamma P / rho) from MUFU seeds + one third-order step
+    (fv2d_sweep.cu: frcp, csound).  Tolerance: 4 ulp (2^-50 relative), six decades of headroom
+    under the 1e-12 parity bar."""
+    rng = np.random.default_rng(7)
+    n = 1 << 20
+    mant = rng.uniform(1.0, 2.0, n)
+    a = mant * np.exp2(rng.integers(-200, 200, n))
+    a[: n // 2] = np.exp(rng.uniform(np.log(1e-6), np.log(1e6), n // 2))  # the physical range, densely
+    a[::7] *= -1.0
+    b = np.exp(rng.uniform(np.log(1e-8), np.log(1e8), n))
+    r, _ = capi.math_probe(a, b)
+    assert np.max(np.abs(r * a - 1.0)) <= 2.0 ** -50
+    assert np.max(np.abs(r - 1.0 / a) / np.abs(1.0 / a)) <= 2.0 ** -50
+    ap = np.abs(a[: n // 2])
+    _, c = capi.math_probe(ap, b[: n // 2])
+    exact = np.sqrt(ap.astype(np.longdouble) / b[: n // 2].astype(np.longdouble))
+    assert float(np.max(np.abs(c.astype(np.longdouble) - exact) / exact)) <= 2.0 ** -50
