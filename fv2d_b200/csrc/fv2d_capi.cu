@@ -197,7 +197,7 @@ static int ensure_ustar(fv2d_ctx *c)
   const size_t bytes = array_bytes(c->kp.L);
   FV2D_CUDA(cudaMalloc(&c->Ustar, bytes));
   FV2D_CUDA(cudaMemsetAsync(c->Ustar, 0, bytes, c->stream));
-  return FV2D_OK;
+  return make_tmap(&c->tmapUstar, c->Ustar, c->kp.L, sweep_strip_width());
 }
 
 // Update.h:176-191 with the operator-level kernels
@@ -302,7 +302,7 @@ static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
     a.Uin = c->U, a.Uout = c->Ustar, a.U0 = nullptr, a.Qout = c->Q[nxt], a.final_stage = 0;
     set_peers(nxt);
     prof_mark(0);
-    e = launch_sweep(c->tmapQ[cur], a, c->stream);
+    e = launch_sweep(c->tmapQ[cur], c->tmapU, a, c->stream);
     prof_mark(1);
     if (e != cudaSuccess)
       return cuda_fail(e, "sweep stage 1", __FILE__, __LINE__);
@@ -316,7 +316,7 @@ static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
     a.Uin = c->Ustar, a.Uout = c->U, a.U0 = c->U, a.Qout = c->Q[cur], a.final_stage = 1;
     set_peers(cur);
     prof_mark(0);
-    e = launch_sweep(c->tmapQ[nxt], a, c->stream);
+    e = launch_sweep(c->tmapQ[nxt], c->tmapUstar, a, c->stream);
     prof_mark(1);
     if (e != cudaSuccess)
       return cuda_fail(e, "sweep stage 2", __FILE__, __LINE__);
@@ -327,7 +327,7 @@ static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
     a.Uin = c->U, a.Uout = c->U, a.U0 = nullptr, a.Qout = c->Q[nxt], a.final_stage = 1;
     set_peers(nxt);
     prof_mark(0);
-    e = launch_sweep(c->tmapQ[cur], a, c->stream);
+    e = launch_sweep(c->tmapQ[cur], c->tmapU, a, c->stream);
     prof_mark(1);
     if (e != cudaSuccess)
       return cuda_fail(e, "sweep", __FILE__, __LINE__);
@@ -653,7 +653,8 @@ int fv2d_ctx_create_slab(const fv2d_device_params *dev, int time_stepping, doubl
 
   FV2D_TRY(sweep_configure());
   c->tmap_ok = (make_tmap(&c->tmapQ[0], c->Q[0], L, sweep_strip_width() + 4) == FV2D_OK) &&
-               (make_tmap(&c->tmapQ[1], c->Q[1], L, sweep_strip_width() + 4) == FV2D_OK);
+               (make_tmap(&c->tmapQ[1], c->Q[1], L, sweep_strip_width() + 4) == FV2D_OK) &&
+               (make_tmap(&c->tmapU, c->U, L, sweep_strip_width()) == FV2D_OK);
   if (!c->tmap_ok)
     return fail(FV2D_ERR_CUDA);
 #undef FV2D_TRY

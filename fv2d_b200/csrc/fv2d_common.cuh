@@ -206,6 +206,7 @@ struct fv2d_ctx
   size_t stage_bytes;
 
   CUtensorMap tmapQ[2]; // TMA descriptors of Q[0], Q[1]
+  CUtensorMap tmapU, tmapUstar; // ... of U and of the RK2 stage array (valid once Ustar exists)
   bool tmap_ok;
   int acc_parity; // which inv_acc slot the NEXT sweep accumulates into
 

@@ -56,9 +56,9 @@ struct SweepArgs
   int lo_rank, hi_rank;
   unsigned long long mail_gen; // generation stamped on this sweep's CFL mail (final stage)
 };
-// tmapQ must describe the array the stage READS (Qin).  Returns cudaSuccess or the launch error;
-// sets *launches to the number of kernels enqueued.
-cudaError_t launch_sweep(const CUtensorMap &tmapQ, const SweepArgs &a, cudaStream_t s);
+// tmapQ / tmapU must describe the arrays the stage READS (Qin: boxes of strip width + 4 columns;
+// Uin: boxes of strip width columns).  Returns cudaSuccess or the launch error.
+cudaError_t launch_sweep(const CUtensorMap &tmapQ, const CUtensorMap &tmapU, const SweepArgs &a, cudaStream_t s);
 // Opt-in dynamic shared memory etc.; call once per process before the first sweep.
 cudaError_t sweep_configure();
 int sweep_strip_width();

@@ -31,6 +31,7 @@
 #include "fv2d_kernels.h"
 
 #include <cstring>
+#include <type_traits>
 
 namespace fv2d
 {
@@ -113,6 +114,9 @@ __device__ __forceinline__ double ldg_stream(const double *ptr, int pred)
 #endif
 #ifndef FV2D_PS_SHORT
 #define FV2D_PS_SHORT 1
+#endif
+#ifndef FV2D_BYTEOFF
+#define FV2D_BYTEOFF 1 // carried per-thread byte offset instead of per-row index arithmetic
 #endif
 
 // 1/a: MUFU.RCP64H seed (relative error e0 <= ~2^-18) + ONE third-order step
@@ -316,16 +320,39 @@ __device__ __forceinline__ FaceFlux riemann_f(const FaceState &L, const FaceStat
     return hllc_f<FACEC>(L, R, entho, gamma);
 }
 
+// Viscous stress flux through ONE face (Viscosity.h:63-107), in the frame of the face normal:
+// n / t = velocity components normal / tangential to the face; hi / lo = the two cells across the
+// face; *_p / *_m = their neighbours one cell up / down the tangential direction.  Normal
+// derivatives are one-sided across the face, tangential ones the 4-point average
+// (Viscosity.h:70-77).  The reference evaluates this expression twice per face (as the `side == 2`
+// face of one cell and the `side == 1` face of the next, same operands in the same order); here
+// every face is done once and the result is folded into the face's Riemann flux.
+struct ViscFlux
+{
+  double n, t, e; // normal momentum, tangential momentum, energy:  tau_nn, tau_nt, tau . q  (x mu later)
+};
+__device__ __forceinline__ ViscFlux visc_face(double n_hi, double n_lo, double t_hi, double t_lo, double n_hi_p,
+                                              double n_hi_m, double n_lo_p, double n_lo_m, double t_hi_p, double t_hi_m,
+                                              double t_lo_p, double t_lo_m, double rdn, double rdt)
+{
+  const double c43 = 4.0 / 3.0, c23 = 2.0 / 3.0;
+  const double dndn = rdn * (n_hi - n_lo);
+  const double dtdn = rdn * (t_hi - t_lo);
+  const double dndt = 0.25 * rdt * (n_hi_p - n_hi_m + n_lo_p - n_lo_m);
+  const double dtdt = 0.25 * rdt * (t_hi_p - t_hi_m + t_lo_p - t_lo_m);
+  const double tnn  = c43 * dndn - c23 * dtdt;
+  const double tnt  = dtdn + dndt;
+  ViscFlux f;
+  f.n = tnn;
+  f.t = tnt;
+  f.e = tnn * (0.5 * (n_hi + n_lo)) + tnt * (0.5 * (t_hi + t_lo));
+  return f;
+}
+
 // --------------------------------------------------------------------------- the kernel
 
-#ifndef FV2D_NS
-#define FV2D_NS 8
-#endif
-#ifndef FV2D_UAHEAD
-#define FV2D_UAHEAD 3
-#endif
-#ifndef FV2D_MINBLOCKS
-#define FV2D_MINBLOCKS(NT) ((NT) <= 128 ? 4 : ((NT) <= 256 ? 2 : 1))
+#ifndef FV2D_NS_BIAS
+#define FV2D_NS_BIAS 0 // development knob: moves ring slots from the U ring to the Q ring
 #endif
 #ifndef FV2D_UNROLL
 #define FV2D_UNROLL 2 // rows per loop body (2 rows = 19 KB of code, inside the 32 KB L1.5 I-cache)
@@ -333,33 +360,65 @@ __device__ __forceinline__ FaceFlux riemann_f(const FaceState &L, const FaceStat
 #ifndef FV2D_EXTRA_SMEM
 #define FV2D_EXTRA_SMEM 0 // development knob: pads the CTA's shared memory to lower the occupancy
 #endif
-constexpr int kNS = FV2D_NS; // ring depth in rows (power of two)
 constexpr int kUnroll = FV2D_UNROLL;
-
-template <int NT>
-struct SweepSmem
+// ---- shared-memory budget of a variant.  Two CTAs per SM leave 113 KB each; after the exchange
+// arrays the rest is cut into 8 KB ring slots, shared between the Q ring and the U ring so that
+// both are requested about equally many rows ahead of their use.
+//   exchange arrays: X2 16 KB; X1 16 KB (PLM only: a PCM face state is the cell state, read from
+//   the Q ring itself); face sound speeds X1c 4 KB (all but PLM + HLLC); temperatures X1T 4 KB
+//   (conduction / viscosity variants)
+__host__ __device__ constexpr int ring_total(bool plm, bool facec, bool diff)
 {
-  double ring[kNS][4][NT]; // TMA destination: [slot][field][column]
-  // exchange arrays, by row parity; fields are paired so that every access is one conflict-free
-  // 128-bit LDS / STS (16-byte stride between neighbouring threads)
-  double2 X1a[2][NT]; // +x face state of each column: (r, n)
-  double2 X1b[2][NT]; //                                (t, p)
-  double X1c[2][NT];  //                                 c   (only when face states carry it)
-  double2 X2a[2][NT]; // x-face flux at the LEFT face of each column: (m, n)
-  double2 X2b[2][NT]; //                                              (t, e)
-  uint64_t full[kNS]; // TMA completion barriers
+  return (115712 - 256 - 16384 - (plm ? 16384 : 0) - (facec ? 4096 : 0) - (diff ? 4096 : 0)) / 8192;
+}
+// Newest Q row that no thread reads any more once the row barrier of iteration k is passed,
+// relative to k: the viscous x-face flux reads rows k-1 .. k+1 in phase B, gravity reads rho of
+// row k in the epilogue; otherwise PLM reads row k+1 last in phase C, PCM row k last in phase B.
+__host__ __device__ constexpr int ring_dead(bool plm, int grav, bool diff) { return (diff || grav != 0) ? -1 : (plm ? 1 : 0); }
+// Q row k+dead+NS is requested in iteration k and first read in iteration k+dead+NS-2; U row
+// k-1+NU is requested in iteration k and read in iteration k-1+NU: balance the two look-aheads.
+__host__ __device__ constexpr int ring_ns(int total, int dead) { return (total + 2 - dead) / 2 + FV2D_NS_BIAS; }
+
+template <bool B, int N>
+struct dim_if
+{
+  static constexpr int value = B ? N : 1;
 };
 
-template <int NT, bool PLM, int SOLVER, bool GRAV, bool DIFF>
+template <int NT, int kNS, int kNU, bool PLM, bool FACEC, bool DIFF>
+struct SweepSmem
+{
+  double ring[kNS][4][NT];  // TMA destination, Q rows: [slot][field][column incl. 2+2 halo]
+  double uring[kNU][4][NT]; // TMA destination, U rows: [slot] then a dense [field][NT-4] box
+  // exchange arrays, by row parity; fields are paired so that every access is one conflict-free
+  // 128-bit LDS / STS (16-byte stride between neighbouring threads)
+  double2 X1a[dim_if<PLM, 2>::value][dim_if<PLM, NT>::value];    // +x face state of each column: (r, n)
+  double2 X1b[dim_if<PLM, 2>::value][dim_if<PLM, NT>::value];    //                                (t, p)
+  double X1c[dim_if<FACEC, 2>::value][dim_if<FACEC, NT>::value]; //                                 c
+  double X1T[dim_if<DIFF, 2>::value][dim_if<DIFF, NT>::value];   // temperature P / rho of each column
+  double2 X2a[2][NT];  // x-face flux at the LEFT face of each column: (m, n)
+  double2 X2b[2][NT];  //                                              (t, e)
+  uint64_t full[kNS];  // TMA completion barriers, one per Q ring slot
+  uint64_t ufull[kNU]; // ... one per U ring slot
+};
+
+// GRAV: 0 = no gravity, 1 = gravity, 2 = gravity + well-balanced flux at the y boundary
+template <int NT, bool PLM, int SOLVER, int GRAV, bool DIFF>
 __global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : (NT <= 256 ? 2 : 1)))
-k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepArgs a)
+k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmU,
+        const __grid_constant__ SweepArgs a)
 {
   constexpr int W = NT - 4;
   // Do the face states carry their sound speed?  Not for PLM + HLLC (see hllc_f); PCM has one
   // sound speed per cell shared by its four faces, HLL / FSLP need both sides'.
   constexpr bool FACEC = !(PLM && SOLVER == FV2D_HLLC);
+  constexpr int kDead = ring_dead(PLM, GRAV, DIFF);
+  constexpr int kNS   = ring_ns(ring_total(PLM, FACEC, DIFF), kDead);
+  constexpr int kNU   = ring_total(PLM, FACEC, DIFF) - kNS;
+  static_assert(kNS + kDead >= 4 && kNU >= 2, "ring too shallow");
+  using Smem = SweepSmem<NT, kNS, kNU, PLM, FACEC, DIFF>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  SweepSmem<NT> &S = *reinterpret_cast<SweepSmem<NT> *>(smem_raw);
+  Smem &S = *reinterpret_cast<Smem *>(smem_raw);
 
   const fv2d_device_params &p = a.kp.p;
   const Layout &L             = a.kp.L;
@@ -378,10 +437,11 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
 #endif
   const int j0    = p.jbeg + cy * a.chunk_rows;
   const int j1    = min(j0 + a.chunk_rows, p.jend); // rows [j0, j1) are updated
-  const int rbase = j0 - 2;                         // first row staged
-  const int rlast = j1 + 1;                         // last row staged
+  const int rbase = j0 - 2;                         // first Q row staged
+  const int rlast = j1 + 1;                         // last Q row staged
   const bool interior = (t >= 2) && (t < NT - 2) && (col < p.iend);
   const int tl = (t > 0 ? t - 1 : 0), tr = (t < NT - 1 ? t + 1 : NT - 1);
+  const int tu = min(max(t - 2, 0), W - 1); // this thread's column inside a U box
 
   const double dt    = a.kp.sc->dt;
   const double rdx   = 1.0 / p.dx;
@@ -397,40 +457,64 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
 #pragma unroll
     for (int s = 0; s < kNS; ++s)
       mbar_init(&S.full[s], 1);
+#pragma unroll
+    for (int s = 0; s < kNU; ++s)
+      mbar_init(&S.ufull[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
 
-  constexpr uint32_t kRowBytes = 4u * NT * sizeof(double);
-  const int tma_x              = L.lead + i0 - 2;
+  // The producer (thread 0) stages Q rows (NT columns x 4 fields, rows rbase .. rlast) and U rows
+  // (W columns x 4 fields, rows j0 .. j1-1) into two independent rings.
+  constexpr uint32_t kQRowBytes = 4u * NT * sizeof(double);
+  constexpr uint32_t kURowBytes = 4u * W * sizeof(double);
+  const int tma_xq     = L.lead + i0 - 2;
+  const int tma_xu     = L.lead + i0;
+  const uint32_t ring0 = smem_u32(&S.ring[0][0][0]);
+  const uint32_t urng0 = smem_u32(&S.uring[0][0][0]);
+  const uint32_t bar0  = smem_u32(&S.full[0]);
+  const uint32_t ubar0 = smem_u32(&S.ufull[0]);
+  auto stage_q = [&](int r, uint32_t slot) {
+    mbar_expect_tx_u32(bar0 + 8u * slot, kQRowBytes);
+    tma_load_3d_u32(ring0 + kQRowBytes * slot, &tmQ, tma_xq, r, 0, bar0 + 8u * slot);
+  };
+  auto stage_u = [&](int r, uint32_t slot) {
+    mbar_expect_tx_u32(ubar0 + 8u * slot, kURowBytes);
+    tma_load_3d_u32(urng0 + kQRowBytes * slot, &tmU, tma_xu, r, 0, ubar0 + 8u * slot);
+  };
   if (t == 0)
   {
     for (int r = rbase; r <= min(rlast, rbase + kNS - 1); ++r)
-    {
-      const int s = r - rbase;
-      mbar_expect_tx(&S.full[s], kRowBytes);
-      tma_load_3d(&S.ring[s][0][0], &tmQ, tma_x, r, 0, &S.full[s]);
-    }
+      stage_q(r, (uint32_t)(r - rbase));
+    for (int r = j0; r <= min(j1 - 1, j0 + kNU - 1); ++r)
+      stage_u(r, (uint32_t)(r - j0));
   }
 
-  auto slot_of  = [&](int r) { return (r - rbase) & (kNS - 1); };
-  auto wait_row = [&](int r) { mbar_wait(&S.full[slot_of(r)], (uint32_t)(((r - rbase) / kNS) & 1)); };
-
-  // ---- pre-prologue: rows j0-2, j0-1, j0 of this column
-  double qk[4], qn[4]; // q(row k), q(row k+1)
-  FaceState yp;        // +y face state of row k (frame of the y normal: n = v, t = u)
-  wait_row(rbase);
-  wait_row(rbase + 1);
-  wait_row(rbase + 2);
+  // ---- pre-prologue: rows j0-2, j0-1, j0 of this column (ring slots 0, 1, 2; first phase)
+  double qn[4]; // q(row k+1)
+  FaceState yp; // +y face state of row k (frame of the y normal: n = v, t = u)
+  double dyl[4]; // q(k+1) - q(k): the lower y difference of row k+1's slope, carried row to row
+  double Tk = 0.0; // temperature P / rho of (col, k) (conduction)
+  // conduction / viscosity, done face by face and folded into the Riemann fluxes: the reference's
+  //   U += dt (vf_x + vf_y)                    (Viscosity.h:112-116, not divided by the cell size: Q8)
+  //   U[IE] += dt/dx (FR - FL) + dt/dy (FD - FU)               (ThermalConduction.h:106)
+  // are differences of face quantities, so  f_x -= dx mu tau_x + kappa dT/dx  etc. gives the same
+  // update through dt/dx (f_left - f_right).
+  const bool tc_on = DIFF && p.thermal_conductivity_active, visc_on = DIFF && p.viscosity_active;
+  const double mudx = p.mu * p.dx, mudy = p.mu * p.dy;
+  const double kaprdx = p.kappa * rdx, kaprdy = p.kappa * rdy;
+  mbar_wait(&S.full[0], 0);
+  mbar_wait(&S.full[1], 0);
+  mbar_wait(&S.full[2], 0);
   {
-    double qa[4];
+    double qa[4], qk[4];
 #pragma unroll
     for (int f = 0; f < 4; ++f)
     {
-      qa[f] = S.ring[slot_of(rbase)][f][t];
-      qk[f] = S.ring[slot_of(rbase + 1)][f][t];
-      qn[f] = S.ring[slot_of(rbase + 2)][f][t];
+      qa[f] = S.ring[0][f][t];
+      qk[f] = S.ring[1][f][t];
+      qn[f] = S.ring[2][f][t];
     }
     double s[4] = {0.0, 0.0, 0.0, 0.0};
     if constexpr (PLM)
@@ -444,77 +528,49 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
     yp.n = fma(0.5, s[2], qk[2]);
     yp.p = fma(0.5, s[3], qk[3]);
     yp.c = FACEC ? csound(gamma * yp.p, yp.r) : 0.0;
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+      dyl[f] = qn[f] - qk[f];
+    if constexpr (DIFF)
+      Tk = qk[3] * frcp(qk[0]);
   }
 
-  double dyl[4]; // q(k+1) - q(k): the lower y difference of row k+1's slope, carried row to row
-#pragma unroll
-  for (int f = 0; f < 4; ++f)
-    dyl[f] = qn[f] - qk[f];
-  FaceFlux fy_lo;  // y-face flux below row k+... (becomes the low face of the next row)
+  FaceFlux fy_lo;  // y-face flux below row k (becomes the low face of the next row)
   FaceState xm;    // -x face state of row k (own cell, left face), frame of the x normal
-  double rho_k = qk[0];
   fy_lo.m = fy_lo.n = fy_lo.t = fy_lo.e = fy_lo.pout = 0.0;
   xm.r = xm.n = xm.t = xm.p = xm.c = 0.0;
 
   const long long ocol = L.at(0, col, 0);
+#if FV2D_BYTEOFF
   // Global addresses = uniform per-(array, field) base + one per-thread byte offset that is
   // carried and bumped by a row pitch per iteration (two integer instructions per address).
   const long long pitchB = (long long)L.pitch * (long long)sizeof(double);
   const long long planeB = L.plane * (long long)sizeof(double);
   long long offB         = (ocol + (long long)(j0 - 1) * L.pitch) * (long long)sizeof(double); // row k
-  const char *const UinB  = reinterpret_cast<const char *>(a.Uin);
-  char *const UoutB       = reinterpret_cast<char *>(a.Uout);
-  char *const QoutB       = reinterpret_cast<char *>(a.Qout);
-  // U rows are pulled into L2 kUAhead rows ahead of their use (one bulk prefetch per field)
-  constexpr int kUAhead     = FV2D_UAHEAD;
-  const int ncols_strip     = min(W, p.iend - i0) & ~1;
-  const uint32_t upf_bytes  = (uint32_t)ncols_strip * (uint32_t)sizeof(double);
-  const double *Ustrip      = a.Uin + L.at(0, i0, 0);
-  // the prefetching thread sits in another warp than the TMA producer (t == 0), so that no
-  // single warp carries all the per-row bookkeeping into the row barrier
-  constexpr int kPfThread = (NT > 32) ? 32 : 0;
-  const bool pf_thread    = (kUAhead > 0) && (t == kPfThread) && (upf_bytes > 0);
-  const char *pf_ptr      = reinterpret_cast<const char *>(Ustrip + (long long)(j0 + kUAhead) * L.pitch); // row k+1+kUAhead
-  if (pf_thread)
-  {
-    for (int r = j0; r < min(j0 + kUAhead, j1); ++r)
-#pragma unroll
-      for (int f = 0; f < 4; ++f)
-        l2_prefetch(Ustrip + f * L.plane + (long long)r * L.pitch, upf_bytes);
-  }
-  const uint32_t ring0 = smem_u32(&S.ring[0][0][0]);
-  const uint32_t bar0  = smem_u32(&S.full[0]);
-  const int k_refill_last = rlast - kNS + 2; // last iteration that still has a row to stage
+#endif
 
   double inv_dt_max = -1.7976931348623157e308;
-  unsigned n_negr = 0, n_negp = 0, n_nan = 0;
 
-  // U of the own column, straight from global memory (coalesced, read once), requested ONE ROW
-  // AHEAD of its use: the load of row k+1 is issued at the top of iteration k, so a full row of
-  // arithmetic (and the row barrier) covers the HBM latency
-  double unx[4] = {0.0, 0.0, 0.0, 0.0};
+  // uniform ring bookkeeping, carried instead of recomputed from k
+  int s2 = 3 % kNS;             // ring slot of Q row k+2
+  uint32_t ph2 = (3 / kNS) & 1; // phase parity of that slot's barrier
+  int s1 = 2, s0 = 1, sm1 = 0;  // ring slots of Q rows k+1, k, k-1
+  int us = kNU - 1;             // U ring slot of row k (row j0 <-> slot 0)
+  uint32_t uph = 1;             // phase parity of that slot's barrier (flips to 0 on entering row j0)
+  int qnext = rbase + kNS, qslot = 0; // producer: next Q row to stage and its ring slot
+  int uslot = 0;                      // producer: ring slot of U row k-1 (refilled with row k-1+NU)
 
   // ---- march: iteration k finishes row k; k = j0-1 is the warm-up (no update)
 #pragma unroll kUnroll
   for (int k = j0 - 1; k < j1; ++k)
   {
     const int par = k & 1;
-    double un[4];
-#pragma unroll
-    for (int f = 0; f < 4; ++f)
-      un[f] = unx[f];
-    {
-      const int pred = interior && (k + 1 < j1);
-#pragma unroll
-      for (int f = 0; f < 4; ++f)
-        unx[f] = ldg_stream(reinterpret_cast<const double *>(UinB + f * planeB + (offB + pitchB)), pred);
-    }
     // A. new row k+2 enters; y slopes / face states of row k+1; y-face flux at k+1/2
-    wait_row(k + 2);
+    mbar_wait(&S.full[s2], ph2);
     double qnn[4];
 #pragma unroll
     for (int f = 0; f < 4; ++f)
-      qnn[f] = S.ring[slot_of(k + 2)][f][t];
+      qnn[f] = S.ring[s2][f][t];
 
     FaceState ym, yp1;
     {
@@ -552,16 +608,61 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
     }
     const double gdy = p.gy * p.dy, gdx = p.gx * p.dx;
     FaceFlux fy_hi = riemann_f<SOLVER, FACEC>(yp, ym, entho, gamma, gdy, p.fslp_K);
+    // diffusive flux through the same face (between rows k and k+1), to be subtracted
+    double dy_t = 0.0, dy_n = 0.0, dy_e = 0.0, Tn = 0.0;
+    if constexpr (DIFF)
+    {
+      if (tc_on)
+      {
+        Tn   = qn[3] * frcp(qn[0]);
+        dy_e = kaprdy * (Tn - Tk); // FD of row k = FU of row k+1 (ThermalConduction.h:66-67)
+      }
+      if (visc_on)
+      {
+        const double u_lo = S.ring[s0][1][t], v_lo = S.ring[s0][2][t];
+        const ViscFlux vf = visc_face(qn[2], v_lo, qn[1], u_lo,                                        //
+                                      S.ring[s1][2][tr], S.ring[s1][2][tl], S.ring[s0][2][tr], S.ring[s0][2][tl], //
+                                      S.ring[s1][1][tr], S.ring[s1][1][tl], S.ring[s0][1][tr], S.ring[s0][1][tl], //
+                                      rdy, rdx);
+        dy_n = mudy * vf.n;
+        dy_t = mudy * vf.t;
+        dy_e = fma(mudy, vf.e, dy_e);
+      }
+    }
 
     // B. x-face flux at the left face of (col, k): left state from the neighbour thread
     //    (also runs, on don't-care data, in the warm-up iteration: no branch, so the x and y
     //    Riemann problems of a row can be scheduled together)
     {
       FaceState xl;
-      const double2 la = S.X1a[par][tl], lb = S.X1b[par][tl];
-      xl.r = la.x, xl.n = la.y, xl.t = lb.x, xl.p = lb.y;
-      xl.c = FACEC ? S.X1c[par][tl] : 0.0;
+      if constexpr (PLM)
+      {
+        const double2 la = S.X1a[par][tl], lb = S.X1b[par][tl];
+        xl.r = la.x, xl.n = la.y, xl.t = lb.x, xl.p = lb.y;
+      }
+      else // PCM: the +x face state of the left neighbour is its cell state, still in the ring
+        xl.r = S.ring[s0][0][tl], xl.n = S.ring[s0][1][tl], xl.t = S.ring[s0][2][tl], xl.p = S.ring[s0][3][tl];
+      if constexpr (FACEC)
+        xl.c = S.X1c[par][tl];
+      else
+        xl.c = 0.0;
       FaceFlux fx = riemann_f<SOLVER, FACEC>(xl, xm, entho, gamma, gdx, p.fslp_K);
+      if constexpr (DIFF)
+      {
+        // diffusive flux through the left x-face of (col, k): cells (col-1, k) and (col, k)
+        if (tc_on)
+          fx.e -= kaprdx * (Tk - S.X1T[par][tl]); // FL (ThermalConduction.h:64)
+        if (visc_on)
+        {
+          const ViscFlux vf = visc_face(S.ring[s0][1][t], S.ring[s0][1][tl], S.ring[s0][2][t], S.ring[s0][2][tl],          //
+                                        S.ring[s1][1][t], S.ring[sm1][1][t], S.ring[s1][1][tl], S.ring[sm1][1][tl], //
+                                        S.ring[s1][2][t], S.ring[sm1][2][t], S.ring[s1][2][tl], S.ring[sm1][2][tl], //
+                                        rdx, rdy);
+          fx.n = fma(-mudx, vf.n, fx.n);
+          fx.t = fma(-mudx, vf.t, fx.t);
+          fx.e = fma(-mudx, vf.e, fx.e);
+        }
+      }
       S.X2a[par][t] = make_double2(fx.m, fx.n);
       S.X2b[par][t] = make_double2(fx.t, fx.e);
     }
@@ -569,13 +670,12 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
     // C. x slopes / face states of row k+1 (published for the neighbour on the right)
     FaceState xm1;
     {
-      const int sl = slot_of(k + 1);
-      double s[4]  = {0.0, 0.0, 0.0, 0.0};
+      double s[4] = {0.0, 0.0, 0.0, 0.0};
       if constexpr (PLM)
       {
 #pragma unroll
         for (int f = 0; f < 4; ++f)
-          s[f] = minmod_f(qn[f] - S.ring[sl][f][tl], S.ring[sl][f][tr] - qn[f]);
+          s[f] = minmod_f(qn[f] - S.ring[s1][f][tl], S.ring[s1][f][tr] - qn[f]);
       }
       xm1.r = fma(-0.5, s[0], qn[0]);
       xm1.n = fma(-0.5, s[1], qn[1]);
@@ -598,31 +698,37 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
         xm1.c = ym.c; // PCM: one sound speed per cell
         xp1.c = ym.c;
       }
-      S.X1a[par ^ 1][t] = make_double2(xp1.r, xp1.n);
-      S.X1b[par ^ 1][t] = make_double2(xp1.t, xp1.p);
+      if constexpr (PLM)
+      {
+        S.X1a[par ^ 1][t] = make_double2(xp1.r, xp1.n);
+        S.X1b[par ^ 1][t] = make_double2(xp1.t, xp1.p);
+      }
       if constexpr (FACEC)
         S.X1c[par ^ 1][t] = xp1.c;
+      if constexpr (DIFF)
+        S.X1T[par ^ 1][t] = Tn;
     }
 
     __syncthreads();
 
-    // E. refill the ring slot of row k-2 (no thread reads it any more) with row k-2+NS
-    if (t == 0 && k >= j0 && k <= k_refill_last)
+    // E. Q rows <= k+kDead and U rows <= k-1 are dead now: refill their slots.  (One Q row per
+    //    iteration in the steady state; the first iteration also recycles the pre-prologue rows.)
+    const int nstage = min(rlast, k + kDead + kNS) - qnext + 1;
+    const bool ustage = (k > j0) && (k - 1 + kNU < j1);
+    if (t == 0)
     {
-      const uint32_t s = (uint32_t)slot_of(k - 2);
-      mbar_expect_tx_u32(bar0 + 8u * s, kRowBytes);
-      tma_load_3d_u32(ring0 + kRowBytes * s, &tmQ, tma_x, k - 2 + kNS, 0, bar0 + 8u * s);
+      for (int n = 0; n < nstage; ++n)
+        stage_q(qnext + n, (uint32_t)((qslot + n) % kNS));
+      if (ustage)
+        stage_u(k - 1 + kNU, (uint32_t)uslot);
     }
-    if constexpr (kUAhead > 0)
+    if (nstage > 0)
     {
-      if (pf_thread && k + 1 + kUAhead < j1)
-      {
-#pragma unroll
-        for (int f = 0; f < 4; ++f)
-          l2_prefetch(pf_ptr + f * planeB, upf_bytes);
-      }
-      pf_ptr += pitchB;
+      qnext += nstage;
+      qslot = (qslot + nstage) % kNS;
     }
+    if (k > j0)
+      uslot = (uslot + 1 == kNU) ? 0 : uslot + 1;
 
     // D. finish row k
     {
@@ -633,29 +739,44 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
         fxr.m = ra.x, fxr.n = ra.y, fxr.t = rb.x, fxr.e = rb.y;
         fxl.m = oa.x, fxl.n = oa.y, fxl.t = ob.x, fxl.e = ob.y;
       }
+      // U^n of the own cell, staged by TMA two rows ago (the slot holds garbage in the warm-up
+      // iteration and for the halo threads: neither stores anything)
+      double un[4];
+      if (k >= j0)
+        mbar_wait(&S.ufull[us], uph);
+      {
+        const double *ub = &S.uring[us][0][0];
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+          un[f] = ub[f * W + tu];
+      }
 
       // y fluxes back in the grid frame: (m, t, n, e) -> (rho, rho u, rho v, E)
+      // (fy_lo already holds hyperbolic minus diffusive flux of the face below; same for fy_hi now)
       double fyl[4] = {fy_lo.m, fy_lo.t, fy_lo.n, fy_lo.e};
-      double fyh[4] = {fy_hi.m, fy_hi.t, fy_hi.n, fy_hi.e};
+      double fyh[4] = {fy_hi.m, fy_hi.t - dy_t, fy_hi.n - dy_n, fy_hi.e - dy_e};
 
-      double gyv = 0.0, gxv = 0.0;
-      if constexpr (GRAV)
+      double gyv = 0.0, gxv = 0.0, rho_k = 0.0;
+      if constexpr (GRAV != 0)
       {
-        gxv = (p.gravity_mode == FV2D_GRAV_CONSTANT) ? p.gx : a.kp.gtab[k];
-        gyv = (p.gravity_mode == FV2D_GRAV_CONSTANT) ? p.gy : a.kp.gtab[k];
-        // well-balanced flux at the global y boundary (Update.h:148-156)
-        if (p.well_balanced_flux_at_y_bc)
+        rho_k = S.ring[s0][0][t];
+        // getGravity (Gravity.h:39-57); GRAV == 2 also covers "well-balanced flux, no gravity" (g = 0)
+        if (p.gravity_mode == FV2D_GRAV_CONSTANT)
+          gxv = p.gx, gyv = p.gy;
+        else if (p.gravity_mode == FV2D_GRAV_ANALYTICAL)
+          gxv = gyv = a.kp.gtab[k];
+      }
+      if constexpr (GRAV == 2)
+      {
+        // well-balanced flux at the global y boundary (Update.h:148-156): replaces the HYPERBOLIC
+        // flux of that face by {0, 0, pout -+ rho g dy, 0}; the diffusive part of the face stays
+        // (for the low face the roll below carried only that part into this row)
+        if (k == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL)
+          fyl[2] += fy_hi.pout - rho_k * gyv * p.dy;
+        else if (k == p.jend - 1 && a.kp.edge_hi == EDGE_PHYSICAL)
         {
-          if (k == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL)
-          {
-            fyl[0] = 0.0, fyl[1] = 0.0, fyl[3] = 0.0;
-            fyl[2] = fy_hi.pout - rho_k * gyv * p.dy;
-          }
-          else if (k == p.jend - 1 && a.kp.edge_hi == EDGE_PHYSICAL)
-          {
-            fyh[0] = 0.0, fyh[1] = 0.0, fyh[3] = 0.0;
-            fyh[2] = fy_lo.pout + rho_k * gyv * p.dy;
-          }
+          fyh[0] = 0.0, fyh[1] = -dy_t, fyh[3] = -dy_e;
+          fyh[2] = (fy_lo.pout + rho_k * gyv * p.dy) - dy_n;
         }
       }
 
@@ -664,7 +785,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
       u4[1] = un[1] + (fxl.n - fxr.n) * dtdx + (fyl[1] - fyh[1]) * dtdy;
       u4[2] = un[2] + (fxl.t - fxr.t) * dtdx + (fyl[2] - fyh[2]) * dtdy;
       u4[3] = un[3] + (fxl.e - fxr.e) * dtdx + (fyl[3] - fyh[3]) * dtdy;
-      if constexpr (GRAV)
+      if constexpr (GRAV != 0)
       {
         // Update.h:161-166: both sweeps add into IV (Q4)
         u4[2] += dt * rho_k * gxv + dt * rho_k * gyv;
@@ -673,87 +794,32 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
 
       if constexpr (DIFF)
       {
-        const int sm = slot_of(k - 1), sc = slot_of(k), sp = slot_of(k + 1);
-        if (p.thermal_conductivity_active)
+        // ThermalConduction.h:77-103: with a temperature boundary condition the reference replaces
+        // the cell's own x-flux FL (at jbeg) / FR (at jend-1) by a y-boundary expression (Q7a) -
+        // for that cell only, not for the neighbour sharing the face.  Reproduced as a correction
+        // to the face-based flux on those two rows.
+        const bool row_lo = (k == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL && p.bctc_ymin != FV2D_BCTC_NONE);
+        const bool row_hi = (k == p.jend - 1 && a.kp.edge_hi == EDGE_PHYSICAL && p.bctc_ymax != FV2D_BCTC_NONE);
+        if (tc_on && (row_lo || row_hi))
         {
-          // ThermalConduction.h:47-106, T = P / rho
-          const double TC = S.ring[sc][3][t] * frcp(S.ring[sc][0][t]);
-          const double TL = S.ring[sc][3][tl] * frcp(S.ring[sc][0][tl]);
-          const double TR = S.ring[sc][3][tr] * frcp(S.ring[sc][0][tr]);
-          const double TU = S.ring[sm][3][t] * frcp(S.ring[sm][0][t]);
-          const double TD = S.ring[sp][3][t] * frcp(S.ring[sp][0][t]);
+          const double TC = S.ring[s0][3][t] * frcp(S.ring[s0][0][t]);
+          const double TL = S.ring[s0][3][tl] * frcp(S.ring[s0][0][tl]);
+          const double TR = S.ring[s0][3][tr] * frcp(S.ring[s0][0][tr]);
           const double kap = p.kappa;
-          double FL = kap * (TC - TL) * rdx;
-          double FR = kap * (TR - TC) * rdx;
-          double FU = kap * (TC - TU) * rdy;
-          double FD = kap * (TD - TC) * rdy;
-          if (k == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL && p.bctc_ymin != FV2D_BCTC_NONE)
+          if (row_lo)
           {
-            if (p.bctc_ymin == FV2D_BCTC_FIXED_TEMPERATURE)
-              FL = kap * 2.0 * (TC - p.bctc_ymin_value) * rdy;
-            else if (p.bctc_ymin == FV2D_BCTC_FIXED_GRADIENT)
-              FL = kap * p.bctc_ymin_value;
+            const double FL = kap * (TC - TL) * rdx;
+            const double FLb =
+                (p.bctc_ymin == FV2D_BCTC_FIXED_TEMPERATURE) ? kap * 2.0 * (TC - p.bctc_ymin_value) * rdy : kap * p.bctc_ymin_value;
+            u4[3] += dtdx * (FL - FLb);
           }
-          if (k == p.jend - 1 && a.kp.edge_hi == EDGE_PHYSICAL && p.bctc_ymax != FV2D_BCTC_NONE)
+          if (row_hi)
           {
-            if (p.bctc_ymax == FV2D_BCTC_FIXED_TEMPERATURE)
-              FR = kap * 2.0 * (p.bctc_ymax_value - TC) * rdy;
-            else if (p.bctc_ymax == FV2D_BCTC_FIXED_GRADIENT)
-              FR = kap * p.bctc_ymax_value;
+            const double FR = kap * (TR - TC) * rdx;
+            const double FRb =
+                (p.bctc_ymax == FV2D_BCTC_FIXED_TEMPERATURE) ? kap * 2.0 * (p.bctc_ymax_value - TC) * rdy : kap * p.bctc_ymax_value;
+            u4[3] += dtdx * (FRb - FR);
           }
-          u4[3] += dtdx * (FR - FL) + dtdy * (FD - FU);
-        }
-        if (p.viscosity_active)
-        {
-          // Viscosity.h:52-117 on the 3x3 (u,v) stencil; not divided by the cell size (Q8)
-          const double mu = p.mu;
-          const double c43 = 4.0 / 3.0, c23 = 2.0 / 3.0;
-          double su[3][3], sv[3][3];
-          const int rs[3] = {sm, sc, sp};
-          const int cs[3] = {tl, t, tr};
-#pragma unroll
-          for (int b = 0; b < 3; ++b)
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-            {
-              su[b][c] = S.ring[rs[b]][1][cs[c]];
-              sv[b][c] = S.ring[rs[b]][2][cs[c]];
-            }
-          double fu = 0.0, fv = 0.0, fe = 0.0;
-#pragma unroll
-          for (int side = 1; side < 3; ++side)
-          {
-            const double sg = (side == 1 ? -mu : mu);
-            {
-              const double qiU = 0.5 * (su[1][side] + su[1][side - 1]);
-              const double qiV = 0.5 * (sv[1][side] + sv[1][side - 1]);
-              const double dudx = rdx * (su[1][side] - su[1][side - 1]);
-              const double dvdx = rdx * (sv[1][side] - sv[1][side - 1]);
-              const double dudy = 0.25 * rdy * (su[2][side] - su[0][side] + su[2][side - 1] - su[0][side - 1]);
-              const double dvdy = 0.25 * rdy * (sv[2][side] - sv[0][side] + sv[2][side - 1] - sv[0][side - 1]);
-              const double txx = c43 * dudx - c23 * dvdy;
-              const double txy = dvdx + dudy;
-              fu += sg * txx;
-              fv += sg * txy;
-              fe += sg * (txx * qiU + txy * qiV);
-            }
-            {
-              const double qiU = 0.5 * (su[side][1] + su[side - 1][1]);
-              const double qiV = 0.5 * (sv[side][1] + sv[side - 1][1]);
-              const double dudy = rdy * (su[side][1] - su[side - 1][1]);
-              const double dvdy = rdy * (sv[side][1] - sv[side - 1][1]);
-              const double dudx = 0.25 * rdx * (su[side][2] - su[side][0] + su[side - 1][2] - su[side - 1][0]);
-              const double dvdx = 0.25 * rdx * (sv[side][2] - sv[side][0] + sv[side - 1][2] - sv[side - 1][0]);
-              const double tyy = c43 * dvdy - c23 * dudx;
-              const double txy = dvdx + dudy;
-              fu += sg * txy;
-              fv += sg * tyy;
-              fe += sg * (txy * qiU + tyy * qiV);
-            }
-          }
-          u4[1] += dt * fu;
-          u4[2] += dt * fv;
-          u4[3] += dt * fe;
         }
       }
 
@@ -763,16 +829,23 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
       if (interior && k >= j0)
 #endif
       {
+#if FV2D_BYTEOFF
+#define FV2D_AT(base, f) (*reinterpret_cast<double *>(reinterpret_cast<char *>(base) + (f) * planeB + offB))
+#define FV2D_CAT(base, f) (*reinterpret_cast<const double *>(reinterpret_cast<const char *>(base) + (f) * planeB + offB))
+#else
+        const long long o = ocol + (long long)k * L.pitch;
+#define FV2D_AT(base, f) ((base)[o + (f) * L.plane])
+#define FV2D_CAT(base, f) ((base)[o + (f) * L.plane])
+#endif
         if (a.U0 != nullptr) // SSP-RK2 combine (Update.h:214-220)
         {
-          const char *U0B = reinterpret_cast<const char *>(a.U0);
 #pragma unroll
           for (int f = 0; f < 4; ++f)
-            u4[f] = 0.5 * (*reinterpret_cast<const double *>(U0B + f * planeB + offB) + u4[f]);
+            u4[f] = 0.5 * (FV2D_CAT(a.U0, f) + u4[f]);
         }
 #pragma unroll
         for (int f = 0; f < 4; ++f)
-          *reinterpret_cast<double *>(UoutB + f * planeB + offB) = u4[f];
+          FV2D_AT(a.Uout, f) = u4[f];
 
         // consToPrim (States.h:32-43)
         const double ir = frcp(u4[0]);
@@ -783,16 +856,17 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
         qo[3] = (u4[3] - 0.5 * u4[0] * (qo[1] * qo[1] + qo[2] * qo[2])) * gm1;
         if (a.final_stage)
         {
-          // checkNegatives (SimInfo.h:612-633)
+          // checkNegatives (SimInfo.h:612-633): counted straight into the device counters on
+          // the (rare) event instead of carrying three counters through the sweep
           if (qo[0] < 0.0)
           {
             qo[0] = a.kp.eps_reset;
-            n_negr++;
+            atomicAdd(&a.kp.sc->neg[0], 1ULL);
           }
           if (qo[3] < 0.0)
           {
             qo[3] = a.kp.eps_reset;
-            n_negp++;
+            atomicAdd(&a.kp.sc->neg[1], 1ULL);
           }
           // computeDt of the new state (ComputeDt.h:30-34); a NaN never wins the Max
           // reduction (Kokkos::Max joins with `>`)
@@ -802,11 +876,16 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
           // NaN count (SimInfo.h:624-631): h is NaN whenever a field is, so the per-field
           // count runs only on that (rare) path
           if (h != h)
-            n_nan += (qo[0] != qo[0]) + (qo[1] != qo[1]) + (qo[2] != qo[2]) + (qo[3] != qo[3]);
+          {
+            const int n = (qo[0] != qo[0]) + (qo[1] != qo[1]) + (qo[2] != qo[2]) + (qo[3] != qo[3]);
+            atomicAdd(&a.kp.sc->neg[2], (unsigned long long)n);
+          }
         }
 #pragma unroll
         for (int f = 0; f < 4; ++f)
-          *reinterpret_cast<double *>(QoutB + f * planeB + offB) = qo[f];
+          FV2D_AT(a.Qout, f) = qo[f];
+#undef FV2D_AT
+#undef FV2D_CAT
         // multi-GPU: the slab's two edge rows are also the neighbour's ghost rows — store them
         // straight into the neighbour's memory (peer mapping over NVLink)
         if (a.peer_lo_Qout != nullptr && k < p.jbeg + 2)
@@ -826,18 +905,29 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
       }
     }
 
-    // roll the column window
+    // roll the column window and the ring bookkeeping
+#if FV2D_BYTEOFF
     offB += pitchB;
-    fy_lo = fy_hi;
-    yp    = yp1;
+#endif
+    fy_lo.m = fy_hi.m, fy_lo.t = fy_hi.t - dy_t, fy_lo.n = fy_hi.n - dy_n, fy_lo.e = fy_hi.e - dy_e;
+    fy_lo.pout = fy_hi.pout;
+    if constexpr (GRAV == 2)
+    {
+      // the face below row jbeg: its hyperbolic flux will be replaced by the well-balanced one
+      if (k + 1 == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL)
+        fy_lo.m = 0.0, fy_lo.t = -dy_t, fy_lo.n = -dy_n, fy_lo.e = -dy_e;
+    }
+    Tk = Tn;
+    yp = yp1;
     xm    = xm1;
-    rho_k = qn[0];
 #pragma unroll
     for (int f = 0; f < 4; ++f)
-    {
-      qk[f] = qn[f];
       qn[f] = qnn[f];
-    }
+    sm1 = s0, s0 = s1, s1 = s2;
+    s2  = (s2 + 1 == kNS) ? 0 : s2 + 1;
+    ph2 ^= (s2 == 0) ? 1u : 0u;
+    us = (us + 1 == kNU) ? 0 : us + 1;
+    uph ^= (us == 0) ? 1u : 0u;
   }
 
   // ---- multi-GPU: tell the neighbours how many of their ghost rows this CTA has delivered
@@ -859,30 +949,16 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ SweepAr
     }
   }
 
-  // ---- CTA reductions: CFL maximum and sanity counters
+  // ---- CTA reduction of the CFL maximum
   if (a.final_stage)
   {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
-    {
       inv_dt_max = fmax(inv_dt_max, __shfl_xor_sync(0xffffffffu, inv_dt_max, o));
-      n_negr += __shfl_xor_sync(0xffffffffu, n_negr, o);
-      n_negp += __shfl_xor_sync(0xffffffffu, n_negp, o);
-      n_nan += __shfl_xor_sync(0xffffffffu, n_nan, o);
-    }
-    __syncthreads(); // X2a is free now: reuse as scratch
+    __syncthreads(); // the exchange arrays are free now: reuse as scratch
     double *red = reinterpret_cast<double *>(&S.X2a[0][0]);
     if ((t & 31) == 0)
       red[t >> 5] = inv_dt_max;
-    if ((t & 31) == 0)
-    {
-      if (n_negr)
-        atomicAdd(&a.kp.sc->neg[0], (unsigned long long)n_negr);
-      if (n_negp)
-        atomicAdd(&a.kp.sc->neg[1], (unsigned long long)n_negp);
-      if (n_nan)
-        atomicAdd(&a.kp.sc->neg[2], (unsigned long long)n_nan);
-    }
     __syncthreads();
     if (t == 0)
     {
@@ -1046,51 +1122,65 @@ void launch_step_begin(const KParams &kp, double *Q, const StepBeginArgs &a, cud
 constexpr int kNT = FV2D_NT;
 int sweep_strip_width() { return kNT - 4; }
 
-template <bool PLM, int SOLVER, bool GRAV, bool DIFF>
-static cudaError_t launch_one(const CUtensorMap &tm, const SweepArgs &a, cudaStream_t s, bool configure_only)
+template <bool PLM, int SOLVER, int GRAV, bool DIFF>
+static cudaError_t launch_one(const CUtensorMap &tmQ, const CUtensorMap &tmU, const SweepArgs &a, cudaStream_t s,
+                              bool configure_only)
 {
   auto kern             = k_sweep<kNT, PLM, SOLVER, GRAV, DIFF>;
-  constexpr size_t smem = sizeof(SweepSmem<kNT>) + FV2D_EXTRA_SMEM;
+  constexpr bool FACEC  = !(PLM && SOLVER == FV2D_HLLC);
+  constexpr int NS = ring_ns(ring_total(PLM, FACEC, DIFF), ring_dead(PLM, GRAV, DIFF));
+  constexpr int NU = ring_total(PLM, FACEC, DIFF) - NS;
+  constexpr size_t smem = sizeof(SweepSmem<kNT, NS, NU, PLM, FACEC, DIFF>) + FV2D_EXTRA_SMEM;
+  static_assert(kNT != 256 || smem <= 115712, "two CTAs per SM need <= 113 KB of shared memory each");
   if (configure_only)
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int W       = kNT - 4;
   const int nstrips = (a.kp.p.Nx + W - 1) / W;
   const int nchunks = (a.kp.p.Ny + a.chunk_rows - 1) / a.chunk_rows;
-  kern<<<dim3(nstrips, nchunks), kNT, smem, s>>>(tm, a);
+  kern<<<dim3(nstrips, nchunks), kNT, smem, s>>>(tmQ, tmU, a);
   return cudaGetLastError();
 }
 
 template <bool PLM, int SOLVER>
-static cudaError_t dispatch2(const CUtensorMap &tm, const SweepArgs &a, cudaStream_t s, bool cfg, bool grav, bool diff)
+static cudaError_t dispatch2(const CUtensorMap &tmQ, const CUtensorMap &tmU, const SweepArgs &a, cudaStream_t s, bool cfg,
+                             int grav, bool diff)
 {
-  if (grav)
-    return diff ? launch_one<PLM, SOLVER, true, true>(tm, a, s, cfg) : launch_one<PLM, SOLVER, true, false>(tm, a, s, cfg);
-  return diff ? launch_one<PLM, SOLVER, false, true>(tm, a, s, cfg) : launch_one<PLM, SOLVER, false, false>(tm, a, s, cfg);
+  switch (grav)
+  {
+  case 0:
+    return diff ? launch_one<PLM, SOLVER, 0, true>(tmQ, tmU, a, s, cfg) : launch_one<PLM, SOLVER, 0, false>(tmQ, tmU, a, s, cfg);
+  case 1:
+    return diff ? launch_one<PLM, SOLVER, 1, true>(tmQ, tmU, a, s, cfg) : launch_one<PLM, SOLVER, 1, false>(tmQ, tmU, a, s, cfg);
+  default:
+    return diff ? launch_one<PLM, SOLVER, 2, true>(tmQ, tmU, a, s, cfg) : launch_one<PLM, SOLVER, 2, false>(tmQ, tmU, a, s, cfg);
+  }
 }
 
 template <bool PLM>
-static cudaError_t dispatch1(const CUtensorMap &tm, const SweepArgs &a, cudaStream_t s, bool cfg, int solver, bool grav,
-                             bool diff)
+static cudaError_t dispatch1(const CUtensorMap &tmQ, const CUtensorMap &tmU, const SweepArgs &a, cudaStream_t s, bool cfg,
+                             int solver, int grav, bool diff)
 {
   switch (solver)
   {
   case FV2D_HLL:
-    return dispatch2<PLM, FV2D_HLL>(tm, a, s, cfg, grav, diff);
+    return dispatch2<PLM, FV2D_HLL>(tmQ, tmU, a, s, cfg, grav, diff);
   case FV2D_FSLP:
-    return dispatch2<PLM, FV2D_FSLP>(tm, a, s, cfg, grav, diff);
+    return dispatch2<PLM, FV2D_FSLP>(tmQ, tmU, a, s, cfg, grav, diff);
   default:
-    return dispatch2<PLM, FV2D_HLLC>(tm, a, s, cfg, grav, diff);
+    return dispatch2<PLM, FV2D_HLLC>(tmQ, tmU, a, s, cfg, grav, diff);
   }
 }
 
-cudaError_t launch_sweep(const CUtensorMap &tmapQ, const SweepArgs &a, cudaStream_t s)
+cudaError_t launch_sweep(const CUtensorMap &tmapQ, const CUtensorMap &tmapU, const SweepArgs &a, cudaStream_t s)
 {
   const fv2d_device_params &p = a.kp.p;
   const bool plm  = (p.reconstruction == FV2D_PLM); // PCM_WB == PCM (Q3)
-  const bool grav = (p.gravity_mode != FV2D_GRAV_NONE);
+  // 0: nothing; 1: gravity source terms; 2: + well-balanced flux at the y boundary (Update.h:148-156,
+  // which the reference applies whatever the gravity mode)
+  const int grav  = p.well_balanced_flux_at_y_bc ? 2 : (p.gravity_mode != FV2D_GRAV_NONE ? 1 : 0);
   const bool diff = p.thermal_conductivity_active || p.viscosity_active;
-  return plm ? dispatch1<true>(tmapQ, a, s, false, p.riemann_solver, grav, diff)
-             : dispatch1<false>(tmapQ, a, s, false, p.riemann_solver, grav, diff);
+  return plm ? dispatch1<true>(tmapQ, tmapU, a, s, false, p.riemann_solver, grav, diff)
+             : dispatch1<false>(tmapQ, tmapU, a, s, false, p.riemann_solver, grav, diff);
 }
 
 cudaError_t sweep_configure()
@@ -1101,11 +1191,11 @@ cudaError_t sweep_configure()
   memset(&a, 0, sizeof a);
   for (int plm = 0; plm < 2; ++plm)
     for (int solver = 0; solver < 3; ++solver)
-      for (int grav = 0; grav < 2; ++grav)
+      for (int grav = 0; grav < 3; ++grav)
         for (int diff = 0; diff < 2; ++diff)
         {
-          cudaError_t e = plm ? dispatch1<true>(dummy, a, nullptr, true, solver, grav, diff)
-                              : dispatch1<false>(dummy, a, nullptr, true, solver, grav, diff);
+          cudaError_t e = plm ? dispatch1<true>(dummy, dummy, a, nullptr, true, solver, grav, diff)
+                              : dispatch1<false>(dummy, dummy, a, nullptr, true, solver, grav, diff);
           if (e != cudaSuccess)
             return e;
         }

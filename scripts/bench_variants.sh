@@ -1,13 +1,13 @@
 #!/bin/bash
 # Developer tool (GPU box): kernel-only bench line for each scratch/lib_*.so given by name.
-#   scripts/bench_variants.sh [--workload W] name1 name2 ...
+#   [BENCH_EXTRA='--nx 8192 --ny 8192'] scripts/bench_variants.sh [--workload W] name1 name2 ...
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 WL=kelvin_helmholtz_8192_plm_hllc
 if [ "$1" == "--workload" ]; then WL=$2; shift 2; fi
 for n in "$@"; do
   lib=scratch/lib_$n.so; [ "$n" == "main" ] && lib=fv2d_b200/libfv2d_b200.so
-  FV2D_B200_LIB=$PWD/$lib timeout 150 python bench.py --workload $WL --steps 40 --warmup 5 --e2e-steps 0 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/var_${WL}_$n.json
+  FV2D_B200_LIB=$PWD/$lib timeout 150 python bench.py --workload $WL --steps 40 --warmup 5 --e2e-steps 0 --no-cpu-baseline $BENCH_EXTRA 2>&1 | tail -1 > gpurun_out/var_${WL}_$n.json
   python - "$n" gpurun_out/var_${WL}_$n.json <<'PY'
 import json,sys
 try:
