@@ -50,6 +50,16 @@ CASES = {
                                        "solvers.time_stepping": "RK2", "run.boundaries_x": "absorbing",
                                        "run.boundaries_y": "reflecting"}, 10),
     "sod_x_300wide": ("sod_x.ini", {"mesh.Nx": 300, "mesh.Ny": 8, "solvers.reconstruction": "plm"}, 10),
+    # well-balanced y-boundary flux (Update.h:148-156) outside its C91 habitat: with PLM + gravity, and
+    # with NO gravity at all (the reference applies it whatever the gravity mode, g = 0)
+    "rt_wb_plm_32x96": ("rayleigh_taylor.ini", {"mesh.Nx": 32, "mesh.Ny": 96,
+                                                "physics.well_balanced_flux_at_y_bc": "true"}, 10),
+    "blast_wb_nograv_48": ("blast.ini", {"mesh.Nx": 48, "mesh.Ny": 48, "run.boundaries_y": "reflecting",
+                                         "physics.well_balanced_flux_at_y_bc": "true"}, 10),
+    "c91_wb_nograv_48x24": ("C91.ini", {"mesh.Nx": 48, "mesh.Ny": 24, "gravity.mode": "none"}, 10),
+    # conduction + viscosity on top of PLM slopes, and with the HLL solver
+    "c91_plm_64x32": ("C91.ini", {"mesh.Nx": 64, "mesh.Ny": 32, "solvers.reconstruction": "plm"}, 10),
+    "c91_hll_48x24": ("C91.ini", {"mesh.Nx": 48, "mesh.Ny": 24, "solvers.riemann_solver": "hll"}, 10),
 }
 
 
