@@ -501,9 +501,10 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
   //   U[IE] += dt/dx (FR - FL) + dt/dy (FD - FU)               (ThermalConduction.h:106)
   // are differences of face quantities, so  f_x -= dx mu tau_x + kappa dT/dx  etc. gives the same
   // update through dt/dx (f_left - f_right).
+  // (branch-free: an inactive operator runs with a zero coefficient, which subtracts exact zeros)
   const bool tc_on = DIFF && p.thermal_conductivity_active, visc_on = DIFF && p.viscosity_active;
-  const double mudx = p.mu * p.dx, mudy = p.mu * p.dy;
-  const double kaprdx = p.kappa * rdx, kaprdy = p.kappa * rdy;
+  const double mudx = visc_on ? p.mu * p.dx : 0.0, mudy = visc_on ? p.mu * p.dy : 0.0;
+  const double kaprdx = tc_on ? p.kappa * rdx : 0.0, kaprdy = tc_on ? p.kappa * rdy : 0.0;
   mbar_wait(&S.full[0], 0);
   mbar_wait(&S.full[1], 0);
   mbar_wait(&S.full[2], 0);
@@ -612,12 +613,8 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
     double dy_t = 0.0, dy_n = 0.0, dy_e = 0.0, Tn = 0.0;
     if constexpr (DIFF)
     {
-      if (tc_on)
-      {
-        Tn   = qn[3] * frcp(qn[0]);
-        dy_e = kaprdy * (Tn - Tk); // FD of row k = FU of row k+1 (ThermalConduction.h:66-67)
-      }
-      if (visc_on)
+      Tn   = qn[3] * frcp(qn[0]);
+      dy_e = kaprdy * (Tn - Tk); // FD of row k = FU of row k+1 (ThermalConduction.h:66-67)
       {
         const double u_lo = S.ring[s0][1][t], v_lo = S.ring[s0][2][t];
         const ViscFlux vf = visc_face(qn[2], v_lo, qn[1], u_lo,                                        //
@@ -650,9 +647,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
       if constexpr (DIFF)
       {
         // diffusive flux through the left x-face of (col, k): cells (col-1, k) and (col, k)
-        if (tc_on)
-          fx.e -= kaprdx * (Tk - S.X1T[par][tl]); // FL (ThermalConduction.h:64)
-        if (visc_on)
+        fx.e -= kaprdx * (Tk - S.X1T[par][tl]); // FL (ThermalConduction.h:64)
         {
           const ViscFlux vf = visc_face(S.ring[s0][1][t], S.ring[s0][1][tl], S.ring[s0][2][t], S.ring[s0][2][tl],          //
                                         S.ring[s1][1][t], S.ring[sm1][1][t], S.ring[s1][1][tl], S.ring[sm1][1][tl], //
@@ -766,19 +761,6 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
         else if (p.gravity_mode == FV2D_GRAV_ANALYTICAL)
           gxv = gyv = a.kp.gtab[k];
       }
-      if constexpr (GRAV == 2)
-      {
-        // well-balanced flux at the global y boundary (Update.h:148-156): replaces the HYPERBOLIC
-        // flux of that face by {0, 0, pout -+ rho g dy, 0}; the diffusive part of the face stays
-        // (for the low face the roll below carried only that part into this row)
-        if (k == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL)
-          fyl[2] += fy_hi.pout - rho_k * gyv * p.dy;
-        else if (k == p.jend - 1 && a.kp.edge_hi == EDGE_PHYSICAL)
-        {
-          fyh[0] = 0.0, fyh[1] = -dy_t, fyh[3] = -dy_e;
-          fyh[2] = (fy_lo.pout + rho_k * gyv * p.dy) - dy_n;
-        }
-      }
 
       double u4[4];
       u4[0] = un[0] + (fxl.m - fxr.m) * dtdx + (fyl[0] - fyh[0]) * dtdy;
@@ -790,6 +772,23 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
         // Update.h:161-166: both sweeps add into IV (Q4)
         u4[2] += dt * rho_k * gxv + dt * rho_k * gyv;
         u4[3] += dt * 0.5 * (fxl.m + fxr.m) * gxv + dt * 0.5 * (fyl[0] + fyh[0]) * gyv;
+      }
+
+      if constexpr (GRAV == 2)
+      {
+        // well-balanced flux at the global y boundary (Update.h:148-156): replaces the HYPERBOLIC
+        // flux of that face by {0, 0, pout -+ rho g dy, 0}; the diffusive part of the face stays.
+        // Applied as an in-place correction on the two rows it concerns (for the low face the
+        // roll below already dropped the hyperbolic part of the carried flux).
+        if (k == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL)
+          u4[2] += dtdy * (fy_hi.pout - rho_k * gyv * p.dy);
+        else if (k == p.jend - 1 && a.kp.edge_hi == EDGE_PHYSICAL)
+        {
+          u4[0] += dtdy * fy_hi.m;
+          u4[1] += dtdy * fy_hi.t;
+          u4[2] += dtdy * (fy_hi.n - (fy_lo.pout + rho_k * gyv * p.dy));
+          u4[3] += dtdy * fy_hi.e - dt * 0.5 * fy_hi.m * gyv;
+        }
       }
 
       if constexpr (DIFF)
@@ -909,14 +908,17 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
 #if FV2D_BYTEOFF
     offB += pitchB;
 #endif
-    fy_lo.m = fy_hi.m, fy_lo.t = fy_hi.t - dy_t, fy_lo.n = fy_hi.n - dy_n, fy_lo.e = fy_hi.e - dy_e;
-    fy_lo.pout = fy_hi.pout;
     if constexpr (GRAV == 2)
     {
-      // the face below row jbeg: its hyperbolic flux will be replaced by the well-balanced one
-      if (k + 1 == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL)
-        fy_lo.m = 0.0, fy_lo.t = -dy_t, fy_lo.n = -dy_n, fy_lo.e = -dy_e;
+      // the face below row jbeg: its hyperbolic flux will be replaced by the well-balanced one, so
+      // only the diffusive part is carried (w is uniform: 1 everywhere else, and 1 * x is exact)
+      const double w = (k + 1 == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL) ? 0.0 : 1.0;
+      fy_lo.m = w * fy_hi.m, fy_lo.t = fma(w, fy_hi.t, -dy_t), fy_lo.n = fma(w, fy_hi.n, -dy_n);
+      fy_lo.e = fma(w, fy_hi.e, -dy_e);
     }
+    else
+      fy_lo.m = fy_hi.m, fy_lo.t = fy_hi.t - dy_t, fy_lo.n = fy_hi.n - dy_n, fy_lo.e = fy_hi.e - dy_e;
+    fy_lo.pout = fy_hi.pout;
     Tk = Tn;
     yp = yp1;
     xm    = xm1;
