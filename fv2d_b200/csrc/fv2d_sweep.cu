@@ -558,8 +558,22 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
   int s1 = 2, s0 = 1, sm1 = 0;  // ring slots of Q rows k+1, k, k-1
   int us = kNU - 1;             // U ring slot of row k (row j0 <-> slot 0)
   uint32_t uph = 1;             // phase parity of that slot's barrier (flips to 0 on entering row j0)
-  int qnext = rbase + kNS, qslot = 0; // producer: next Q row to stage and its ring slot
-  int uslot = 0;                      // producer: ring slot of U row k-1 (refilled with row k-1+NU)
+  int qslot = 0; // producer: ring slot of the next Q row to stage (row k + kDead + NS in iteration k)
+  int uslot = 0; // producer: ring slot of U row k-1 (refilled with row k-1+NU)
+  if constexpr (kDead >= 0)
+  {
+    // the rows only the pre-prologue needed (rbase .. rbase+kDead) are dead once every thread has
+    // read its column: recycle their slots before the march starts
+    __syncthreads();
+    if (t == 0)
+    {
+#pragma unroll
+      for (int n = 0; n <= kDead; ++n)
+        if (rbase + kNS + n <= rlast)
+          stage_q(rbase + kNS + n, (uint32_t)n);
+    }
+    qslot = (kDead + 1) % kNS;
+  }
 
   // ---- march: iteration k finishes row k; k = j0-1 is the warm-up (no update)
 #pragma unroll kUnroll
@@ -706,22 +720,15 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
 
     __syncthreads();
 
-    // E. Q rows <= k+kDead and U rows <= k-1 are dead now: refill their slots.  (One Q row per
-    //    iteration in the steady state; the first iteration also recycles the pre-prologue rows.)
-    const int nstage = min(rlast, k + kDead + kNS) - qnext + 1;
-    const bool ustage = (k > j0) && (k - 1 + kNU < j1);
+    // E. Q rows <= k+kDead and U rows <= k-1 are dead now: refill their slots
     if (t == 0)
     {
-      for (int n = 0; n < nstage; ++n)
-        stage_q(qnext + n, (uint32_t)((qslot + n) % kNS));
-      if (ustage)
+      if (k + kDead + kNS <= rlast)
+        stage_q(k + kDead + kNS, (uint32_t)qslot);
+      if ((k > j0) && (k - 1 + kNU < j1))
         stage_u(k - 1 + kNU, (uint32_t)uslot);
     }
-    if (nstage > 0)
-    {
-      qnext += nstage;
-      qslot = (qslot + nstage) % kNS;
-    }
+    qslot = (qslot + 1 == kNS) ? 0 : qslot + 1;
     if (k > j0)
       uslot = (uslot + 1 == kNU) ? 0 : uslot + 1;
 
