@@ -416,6 +416,10 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
   constexpr int kNS   = ring_ns(ring_total(PLM, FACEC, DIFF), kDead);
   constexpr int kNU   = ring_total(PLM, FACEC, DIFF) - kNS;
   static_assert(kNS + kDead >= 4 && kNU >= 2, "ring too shallow");
+#ifndef FV2D_UPRODUCER
+#define FV2D_UPRODUCER 0 // (a second producer thread in another warp measured 0.5 % slower)
+#endif
+  constexpr int kUProducer = (NT > FV2D_UPRODUCER) ? FV2D_UPRODUCER : 0; // thread that stages the U rows
   using Smem = SweepSmem<NT, kNS, kNU, PLM, FACEC, DIFF>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem &S = *reinterpret_cast<Smem *>(smem_raw);
@@ -721,13 +725,10 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
     __syncthreads();
 
     // E. Q rows <= k+kDead and U rows <= k-1 are dead now: refill their slots
-    if (t == 0)
-    {
-      if (k + kDead + kNS <= rlast)
-        stage_q(k + kDead + kNS, (uint32_t)qslot);
-      if ((k > j0) && (k - 1 + kNU < j1))
-        stage_u(k - 1 + kNU, (uint32_t)uslot);
-    }
+    if (t == 0 && k + kDead + kNS <= rlast)
+      stage_q(k + kDead + kNS, (uint32_t)qslot);
+    if (t == kUProducer && (k > j0) && (k - 1 + kNU < j1))
+      stage_u(k - 1 + kNU, (uint32_t)uslot);
     qslot = (qslot + 1 == kNS) ? 0 : qslot + 1;
     if (k > j0)
       uslot = (uslot + 1 == kNU) ? 0 : uslot + 1;
