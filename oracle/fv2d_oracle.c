@@ -3,7 +3,7 @@
  * Plain-C restatement of the reference's per-timestep update.  The expression order of
  * every formula follows the reference source so that, compiled without FMA contraction
  * (-ffp-contract=off, x86-64 baseline), results are bit-identical to the reference's
- * Kokkos-OpenMP Release build (checked in tests/test_oracle_vs_reference.py against the
+ * Kokkos-OpenMP Release build (checked in tests/test_init_and_oracle.py against the
  * dumps in tests/golden/).
  */
 #include "fv2d_oracle.h"
