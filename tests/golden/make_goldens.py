@@ -60,6 +60,10 @@ CASES = {
     # conduction + viscosity on top of PLM slopes, and with the HLL solver
     "c91_plm_64x32": ("C91.ini", {"mesh.Nx": 64, "mesh.Ny": 32, "solvers.reconstruction": "plm"}, 10),
     "c91_hll_48x24": ("C91.ini", {"mesh.Nx": 48, "mesh.Ny": 24, "solvers.riemann_solver": "hll"}, 10),
+    "rt_fslp_pcm_32x96": ("rayleigh_taylor.ini", {"mesh.Nx": 32, "mesh.Ny": 96, "solvers.riemann_solver": "fslp",
+                                                  "solvers.reconstruction": "pcm"}, 10),
+    "c91_fslp_plm_48x24": ("C91.ini", {"mesh.Nx": 48, "mesh.Ny": 24, "solvers.riemann_solver": "fslp",
+                                       "solvers.reconstruction": "plm"}, 10),
 }
 
 
