@@ -215,7 +215,7 @@ __device__ __forceinline__ FaceFlux hllc_f(const FaceState &L, const FaceState &
   const double rcL = L.r * (L.n - SL);
   const double rcR = R.r * (SR - R.n);
   const double inv = frcp(rcR + rcL);
-  const double uS  = (rcR * R.n + rcL * L.n + (L.p - R.p)) * inv;
+  const double uS  = fma(rcR, R.n, fma(rcL, L.n, L.p - R.p)) * inv;
 #if FV2D_PS_SHORT
   // p* = pL + rhoL (SL - uL)(u* - uL)  (Toro 10.36; algebraically the reference's
   // (rcR pL + rcL pR + rcL rcR (uL - uR)) / (rcL + rcR), RiemannSolvers.h:83): 2 instructions
@@ -224,8 +224,13 @@ __device__ __forceinline__ FaceFlux hllc_f(const FaceState &L, const FaceState &
   const double pS  = (rcR * L.p + rcL * R.p + rcL * rcR * (L.n - R.n)) * inv;
 #endif
 
-  const bool left = (SL > 0.0) || (uS > 0.0);
-  const bool star = left ? !(SL > 0.0) : (SR > 0.0);
+  // The three wave-speed tests of RiemannSolvers.h:93-122 read sign bits on the integer pipe
+  // instead of DSETPs on the fp64 pipe.  They differ from "> 0" only for an exact +0, where
+  // the two fluxes on either side of the test coincide (F*K = FK when SK = 0; both star fluxes
+  // are (0, p*, 0, 0) when u* = 0).
+  const bool SLpos = __double2hiint(SL) >= 0, uSpos = __double2hiint(uS) >= 0, SRpos = __double2hiint(SR) >= 0;
+  const bool left = SLpos || uSpos;
+  const bool star = left ? !SLpos : SRpos;
 
   const double rK = left ? L.r : R.r;
   const double uK = left ? L.n : R.n;
@@ -450,6 +455,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
   const double dt    = a.kp.sc->dt;
   const double rdx   = 1.0 / p.dx;
   const double rdy   = 1.0 / p.dy;
+  const double rdxy  = rdx + rdy;
   const double dtdx  = dt / p.dx;
   const double dtdy  = dt / p.dy;
   const double gamma = p.gamma0;
@@ -562,8 +568,9 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
   int s1 = 2, s0 = 1, sm1 = 0;  // ring slots of Q rows k+1, k, k-1
   int us = kNU - 1;             // U ring slot of row k (row j0 <-> slot 0)
   uint32_t uph = 1;             // phase parity of that slot's barrier (flips to 0 on entering row j0)
-  int qslot = 0; // producer: ring slot of the next Q row to stage (row k + kDead + NS in iteration k)
-  int uslot = 0; // producer: ring slot of U row k-1 (refilled with row k-1+NU)
+  // (the producer needs no counters of its own: Q row k+kDead+NS goes into the slot of row k+kDead,
+  //  U row k-1+NU into the slot of row k-1)
+  int us_prev = 0; // U ring slot of row k-1
   if constexpr (kDead >= 0)
   {
     // the rows only the pre-prologue needed (rbase .. rbase+kDead) are dead once every thread has
@@ -576,7 +583,6 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
         if (rbase + kNS + n <= rlast)
           stage_q(rbase + kNS + n, (uint32_t)n);
     }
-    qslot = (kDead + 1) % kNS;
   }
 
   // ---- march: iteration k finishes row k; k = j0-1 is the warm-up (no update)
@@ -726,12 +732,9 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
 
     // E. Q rows <= k+kDead and U rows <= k-1 are dead now: refill their slots
     if (t == 0 && k + kDead + kNS <= rlast)
-      stage_q(k + kDead + kNS, (uint32_t)qslot);
+      stage_q(k + kDead + kNS, (uint32_t)(kDead == 1 ? s1 : (kDead == 0 ? s0 : sm1)));
     if (t == kUProducer && (k > j0) && (k - 1 + kNU < j1))
-      stage_u(k - 1 + kNU, (uint32_t)uslot);
-    qslot = (qslot + 1 == kNS) ? 0 : qslot + 1;
-    if (k > j0)
-      uslot = (uslot + 1 == kNU) ? 0 : uslot + 1;
+      stage_u(k - 1 + kNU, (uint32_t)us_prev);
 
     // D. finish row k
     {
@@ -860,25 +863,29 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
         qo[0] = u4[0];
         qo[1] = u4[1] * ir;
         qo[2] = u4[2] * ir;
-        qo[3] = (u4[3] - 0.5 * u4[0] * (qo[1] * qo[1] + qo[2] * qo[2])) * gm1;
+        qo[3] = fma(-0.5, fma(u4[2], qo[2], u4[1] * qo[1]), u4[3]) * gm1; // E - (rho u . u) / 2
         if (a.final_stage)
         {
           // checkNegatives (SimInfo.h:612-633): counted straight into the device counters on
-          // the (rare) event instead of carrying three counters through the sweep
-          if (qo[0] < 0.0)
+          // the (rare) event instead of carrying three counters through the sweep; one integer
+          // test of the two sign bits guards both comparisons
+          if ((__double2hiint(qo[0]) | __double2hiint(qo[3])) < 0)
           {
-            qo[0] = a.kp.eps_reset;
-            atomicAdd(&a.kp.sc->neg[0], 1ULL);
-          }
-          if (qo[3] < 0.0)
-          {
-            qo[3] = a.kp.eps_reset;
-            atomicAdd(&a.kp.sc->neg[1], 1ULL);
+            if (qo[0] < 0.0)
+            {
+              qo[0] = a.kp.eps_reset;
+              atomicAdd(&a.kp.sc->neg[0], 1ULL);
+            }
+            if (qo[3] < 0.0)
+            {
+              qo[3] = a.kp.eps_reset;
+              atomicAdd(&a.kp.sc->neg[1], 1ULL);
+            }
           }
           // computeDt of the new state (ComputeDt.h:30-34); a NaN never wins the Max
           // reduction (Kokkos::Max joins with `>`)
           const double cs = csound(gamma * qo[3], qo[0]);
-          const double h  = (cs + fabs(qo[1])) * rdx + (cs + fabs(qo[2])) * rdy;
+          const double h  = fma(cs, rdxy, fma(fabs(qo[1]), rdx, fabs(qo[2]) * rdy));
           inv_dt_max      = (h > inv_dt_max) ? h : inv_dt_max;
           // NaN count (SimInfo.h:624-631): h is NaN whenever a field is, so the per-field
           // count runs only on that (rare) path
@@ -936,6 +943,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
     sm1 = s0, s0 = s1, s1 = s2;
     s2  = (s2 + 1 == kNS) ? 0 : s2 + 1;
     ph2 ^= (s2 == 0) ? 1u : 0u;
+    us_prev = us;
     us = (us + 1 == kNU) ? 0 : us + 1;
     uph ^= (us == 0) ? 1u : 0u;
   }
