@@ -408,7 +408,10 @@ struct SweepSmem
 };
 
 // GRAV: 0 = no gravity, 1 = gravity, 2 = gravity + well-balanced flux at the y boundary
-template <int NT, bool PLM, int SOLVER, int GRAV, bool DIFF>
+// PLAIN: the common launch - the only stage of a forward-Euler step on a slab without neighbours -
+// whose loop-invariant tests (RK2 combine, peer pushes, final_stage) are resolved at compile time
+// instead of once per row.
+template <int NT, bool PLM, int SOLVER, int GRAV, bool DIFF, bool PLAIN>
 __global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : (NT <= 256 ? 2 : 1)))
 k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmU,
         const __grid_constant__ SweepArgs a)
@@ -431,6 +434,10 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
 
   const fv2d_device_params &p = a.kp.p;
   const Layout &L             = a.kp.L;
+  const double *const U0      = PLAIN ? nullptr : a.U0;
+  const bool final_stage      = PLAIN ? true : (a.final_stage != 0);
+  double *const peer_lo       = PLAIN ? nullptr : a.peer_lo_Qout;
+  double *const peer_hi       = PLAIN ? nullptr : a.peer_hi_Qout;
 
   const int t     = threadIdx.x;
   const int strip = blockIdx.x;
@@ -439,7 +446,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
   // chunk order: when the slab has neighbours the two edge chunks are dispatched first, so
   // their ghost-row pushes travel over NVLink while the interior chunks compute
   int cy = blockIdx.y;
-  if ((a.peer_lo_Qout != nullptr || a.peer_hi_Qout != nullptr) && gridDim.y > 1)
+  if ((peer_lo != nullptr || peer_hi != nullptr) && gridDim.y > 1)
     cy = (cy == 0) ? 0 : (cy == 1 ? (int)gridDim.y - 1 : cy - 1);
 #ifdef FV2D_TEST_NOMEM
   cy = 0;
@@ -847,11 +854,11 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
 #define FV2D_AT(base, f) ((base)[o + (f) * L.plane])
 #define FV2D_CAT(base, f) ((base)[o + (f) * L.plane])
 #endif
-        if (a.U0 != nullptr) // SSP-RK2 combine (Update.h:214-220)
+        if (U0 != nullptr) // SSP-RK2 combine (Update.h:214-220)
         {
 #pragma unroll
           for (int f = 0; f < 4; ++f)
-            u4[f] = 0.5 * (FV2D_CAT(a.U0, f) + u4[f]);
+            u4[f] = 0.5 * (FV2D_CAT(U0, f) + u4[f]);
         }
 #pragma unroll
         for (int f = 0; f < 4; ++f)
@@ -864,7 +871,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
         qo[1] = u4[1] * ir;
         qo[2] = u4[2] * ir;
         qo[3] = fma(-0.5, fma(u4[2], qo[2], u4[1] * qo[1]), u4[3]) * gm1; // E - (rho u . u) / 2
-        if (a.final_stage)
+        if (final_stage)
         {
           // checkNegatives (SimInfo.h:612-633): counted straight into the device counters on
           // the (rare) event instead of carrying three counters through the sweep; one integer
@@ -902,19 +909,19 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
 #undef FV2D_CAT
         // multi-GPU: the slab's two edge rows are also the neighbour's ghost rows — store them
         // straight into the neighbour's memory (peer mapping over NVLink)
-        if (a.peer_lo_Qout != nullptr && k < p.jbeg + 2)
+        if (peer_lo != nullptr && k < p.jbeg + 2)
         {
           const long long op = ocol + (long long)(p.Ny + k) * L.pitch; // its high ghost rows
 #pragma unroll
           for (int f = 0; f < 4; ++f)
-            a.peer_lo_Qout[op + f * L.plane] = qo[f];
+            peer_lo[op + f * L.plane] = qo[f];
         }
-        if (a.peer_hi_Qout != nullptr && k >= p.jend - 2)
+        if (peer_hi != nullptr && k >= p.jend - 2)
         {
           const long long op = ocol + (long long)(k - p.Ny) * L.pitch; // its low ghost rows
 #pragma unroll
           for (int f = 0; f < 4; ++f)
-            a.peer_hi_Qout[op + f * L.plane] = qo[f];
+            peer_hi[op + f * L.plane] = qo[f];
         }
       }
     }
@@ -949,10 +956,10 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
   }
 
   // ---- multi-GPU: tell the neighbours how many of their ghost rows this CTA has delivered
-  if (a.peer_lo_Qout != nullptr || a.peer_hi_Qout != nullptr)
+  if (peer_lo != nullptr || peer_hi != nullptr)
   {
-    const int n_lo = (a.peer_lo_Qout != nullptr) ? max(0, min(j1, p.jbeg + 2) - j0) : 0;
-    const int n_hi = (a.peer_hi_Qout != nullptr) ? max(0, j1 - max(j0, p.jend - 2)) : 0;
+    const int n_lo = (peer_lo != nullptr) ? max(0, min(j1, p.jbeg + 2) - j0) : 0;
+    const int n_hi = (peer_hi != nullptr) ? max(0, j1 - max(j0, p.jend - 2)) : 0;
     if (n_lo + n_hi > 0)
     {
       __threadfence_system();
@@ -968,7 +975,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
   }
 
   // ---- CTA reduction of the CFL maximum
-  if (a.final_stage)
+  if (final_stage)
   {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
@@ -1140,11 +1147,11 @@ void launch_step_begin(const KParams &kp, double *Q, const StepBeginArgs &a, cud
 constexpr int kNT = FV2D_NT;
 int sweep_strip_width() { return kNT - 4; }
 
-template <bool PLM, int SOLVER, int GRAV, bool DIFF>
-static cudaError_t launch_one(const CUtensorMap &tmQ, const CUtensorMap &tmU, const SweepArgs &a, cudaStream_t s,
-                              bool configure_only)
+template <bool PLM, int SOLVER, int GRAV, bool DIFF, bool PLAIN>
+static cudaError_t launch_variant(const CUtensorMap &tmQ, const CUtensorMap &tmU, const SweepArgs &a, cudaStream_t s,
+                                  bool configure_only)
 {
-  auto kern             = k_sweep<kNT, PLM, SOLVER, GRAV, DIFF>;
+  auto kern             = k_sweep<kNT, PLM, SOLVER, GRAV, DIFF, PLAIN>;
   constexpr bool FACEC  = !(PLM && SOLVER == FV2D_HLLC);
   constexpr int NS = ring_ns(ring_total(PLM, FACEC, DIFF), ring_dead(PLM, GRAV, DIFF));
   constexpr int NU = ring_total(PLM, FACEC, DIFF) - NS;
@@ -1157,6 +1164,20 @@ static cudaError_t launch_one(const CUtensorMap &tmQ, const CUtensorMap &tmU, co
   const int nchunks = (a.kp.p.Ny + a.chunk_rows - 1) / a.chunk_rows;
   kern<<<dim3(nstrips, nchunks), kNT, smem, s>>>(tmQ, tmU, a);
   return cudaGetLastError();
+}
+
+template <bool PLM, int SOLVER, int GRAV, bool DIFF>
+static cudaError_t launch_one(const CUtensorMap &tmQ, const CUtensorMap &tmU, const SweepArgs &a, cudaStream_t s,
+                              bool configure_only)
+{
+  if (configure_only)
+  {
+    cudaError_t e = launch_variant<PLM, SOLVER, GRAV, DIFF, true>(tmQ, tmU, a, s, true);
+    return e != cudaSuccess ? e : launch_variant<PLM, SOLVER, GRAV, DIFF, false>(tmQ, tmU, a, s, true);
+  }
+  const bool plain = a.final_stage && a.U0 == nullptr && a.peer_lo_Qout == nullptr && a.peer_hi_Qout == nullptr;
+  return plain ? launch_variant<PLM, SOLVER, GRAV, DIFF, true>(tmQ, tmU, a, s, false)
+               : launch_variant<PLM, SOLVER, GRAV, DIFF, false>(tmQ, tmU, a, s, false);
 }
 
 template <bool PLM, int SOLVER>
