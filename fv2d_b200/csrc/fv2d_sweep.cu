@@ -366,6 +366,10 @@ __device__ __forceinline__ ViscFlux visc_face(double n_hi, double n_lo, double t
 #define FV2D_EXTRA_SMEM 0 // development knob: pads the CTA's shared memory to lower the occupancy
 #endif
 constexpr int kUnroll = FV2D_UNROLL;
+#ifndef FV2D_UNROLL_DIFF
+#define FV2D_UNROLL_DIFF 3 // ... for the conduction / viscosity variants (measured: C91 -2 % vs 2)
+#endif
+constexpr int kUnrollDiff = FV2D_UNROLL_DIFF;
 // ---- shared-memory budget of a variant.  Two CTAs per SM leave 113 KB each; after the exchange
 // arrays the rest is cut into 8 KB ring slots, shared between the Q ring and the U ring so that
 // both are requested about equally many rows ahead of their use.
@@ -382,7 +386,8 @@ __host__ __device__ constexpr int ring_total(bool plm, bool facec, bool diff)
 __host__ __device__ constexpr int ring_dead(bool plm, int grav, bool diff) { return (diff || grav != 0) ? -1 : (plm ? 1 : 0); }
 // Q row k+dead+NS is requested in iteration k and first read in iteration k+dead+NS-2; U row
 // k-1+NU is requested in iteration k and read in iteration k-1+NU: balance the two look-aheads.
-__host__ __device__ constexpr int ring_ns(int total, int dead) { return (total + 2 - dead) / 2 + FV2D_NS_BIAS; }
+// (The conduction / viscosity variants measured 1-2 % faster with one slot moved to the U ring.)
+__host__ __device__ constexpr int ring_ns(int total, int dead, bool diff) { return (total + 2 - dead) / 2 + FV2D_NS_BIAS - (diff ? 1 : 0); }
 
 template <bool B, int N>
 struct dim_if
@@ -421,7 +426,8 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
   // sound speed per cell shared by its four faces, HLL / FSLP need both sides'.
   constexpr bool FACEC = !(PLM && SOLVER == FV2D_HLLC);
   constexpr int kDead = ring_dead(PLM, GRAV, DIFF);
-  constexpr int kNS   = ring_ns(ring_total(PLM, FACEC, DIFF), kDead);
+  constexpr int kUnrollV = DIFF ? kUnrollDiff : kUnroll;
+  constexpr int kNS   = ring_ns(ring_total(PLM, FACEC, DIFF), kDead, DIFF);
   constexpr int kNU   = ring_total(PLM, FACEC, DIFF) - kNS;
   static_assert(kNS + kDead >= 4 && kNU >= 2, "ring too shallow");
 #ifndef FV2D_UPRODUCER
@@ -593,7 +599,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
   }
 
   // ---- march: iteration k finishes row k; k = j0-1 is the warm-up (no update)
-#pragma unroll kUnroll
+#pragma unroll kUnrollV
   for (int k = j0 - 1; k < j1; ++k)
   {
     const int par = k & 1;
@@ -1153,7 +1159,7 @@ static cudaError_t launch_variant(const CUtensorMap &tmQ, const CUtensorMap &tmU
 {
   auto kern             = k_sweep<kNT, PLM, SOLVER, GRAV, DIFF, PLAIN>;
   constexpr bool FACEC  = !(PLM && SOLVER == FV2D_HLLC);
-  constexpr int NS = ring_ns(ring_total(PLM, FACEC, DIFF), ring_dead(PLM, GRAV, DIFF));
+  constexpr int NS = ring_ns(ring_total(PLM, FACEC, DIFF), ring_dead(PLM, GRAV, DIFF), DIFF);
   constexpr int NU = ring_total(PLM, FACEC, DIFF) - NS;
   constexpr size_t smem = sizeof(SweepSmem<kNT, NS, NU, PLM, FACEC, DIFF>) + FV2D_EXTRA_SMEM;
   static_assert(kNT != 256 || smem <= 115712, "two CTAs per SM need <= 113 KB of shared memory each");
