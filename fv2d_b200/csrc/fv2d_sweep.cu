@@ -11,10 +11,10 @@
 // Work decomposition ("column sweep"): the domain is cut into strips of W = NT-4 columns
 // and chunks of `chunk_rows` rows; one CTA of NT threads owns one (strip, chunk).  Thread t
 // owns column i0-2+t of the strip (2 halo columns each side) and marches through the rows:
-//   * Q rows (primitive SoA tile row + its 2-cell x halo, 4 fields) are staged into a
-//     shared-memory ring by TMA (one cp.async.bulk.tensor.3d box of NT x 1 x 4 doubles per
-//     row, completion on an mbarrier), NS rows deep, so HBM latency is hidden without
-//     spending registers on in-flight loads;
+//   * Q rows (primitive SoA tile row + its 2-cell x halo, 4 fields) and U rows (the strip's own
+//     cells) are staged into two shared-memory rings by TMA (one cp.async.bulk.tensor.3d box per
+//     row and ring, completion on mbarriers), several rows ahead, so HBM latency is hidden
+//     without spending registers or address arithmetic on in-flight loads;
 //   * the y-direction stencil lives in registers (each thread keeps the rolling
 //     q(j), q(j+1), the reconstructed +y face state and the y-face flux of its column): every
 //     y-face flux is computed exactly once;
@@ -23,7 +23,8 @@
 //     through small double-buffered shared arrays with ONE __syncthreads per row: every
 //     x-face flux is computed exactly once (by the thread on its right);
 //   * each slope, each face state, each sound speed is computed once per cell; divisions
-//     and square roots are MUFU seeds + Newton/Goldschmidt steps (no IEEE slow paths);
+//     and square roots are MUFU seeds + one third-order correction (no IEEE slow paths);
+//   * conduction and viscosity are evaluated face by face and folded into the face fluxes;
 //   * the epilogue of a row writes U^{n+1}, converts to primitives, applies the
 //     negative-density/pressure reset, accumulates the CFL maximum, writes Q^{n+1}.
 // The per-CTA CFL maximum goes to a device scalar with one atomicMax: the next dt never
@@ -44,10 +45,6 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
   asm volatile("{\n"
@@ -61,15 +58,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
                "r"(parity)
                : "memory");
 }
-// TMA: global (3-D tensor map: column, row, field) -> shared, completion on mbarrier
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, int x, int y, int z, uint64_t *bar)
-{
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-               ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
-               : "memory");
-}
-
-// Same, on precomputed shared-window addresses (keeps the producer's per-row work short)
+// expect_tx / TMA load (3-D tensor map: column, row, field -> shared, completion on an mbarrier)
+// on precomputed shared-window addresses (keeps the producer's per-row work short)
 __device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes)
 {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -79,30 +69,6 @@ __device__ __forceinline__ void tma_load_3d_u32(uint32_t dst, const CUtensorMap 
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar)
                : "memory");
-}
-
-// Asks the L2 to fetch `bytes` (multiple of 16) starting at the 16-byte aligned `ptr`
-// (SASS: UBLKPF).  Used to pull the U rows a few rows ahead of the sweep so the later
-// per-thread loads hit in L2 instead of paying the loaded-HBM latency.
-__device__ __forceinline__ void l2_prefetch(const void *ptr, uint32_t bytes)
-{
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
-}
-
-// Predicated fp64 global load issued HERE (asm volatile keeps it above the row barrier), so
-// the HBM latency overlaps the whole row of arithmetic instead of stalling the first use.
-__device__ __forceinline__ double ldg_stream(const double *ptr, int pred)
-{
-  double v;
-  asm volatile("{\n"
-               ".reg .pred p;\n"
-               "setp.ne.b32 p, %2, 0;\n"
-               "mov.f64 %0, 0d0000000000000000;\n"
-               "@p ld.global.L1::no_allocate.f64 %0, [%1];\n"
-               "}\n"
-               : "=d"(v)
-               : "l"(ptr), "r"(pred));
-  return v;
 }
 
 // Development knobs for the A/B variants built by scripts/build_variant.sh (defaults = shipped).

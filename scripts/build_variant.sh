@@ -12,4 +12,4 @@ $NVCC -std=c++17 -O3 $ARCH -lineinfo -Xcompiler -fPIC -Xcudafe --diag_suppress=1
   -c fv2d_b200/csrc/fv2d_sweep.cu -o build/fv2d_sweep_$name.o 2> build/fv2d_sweep_$name.ptxas.log
 make -s build/fv2d_ops.o build/fv2d_capi.o
 $NVCC $ARCH -shared -o scratch/lib_$name.so build/fv2d_ops.o build/fv2d_sweep_$name.o build/fv2d_capi.o -cudart static -Xcompiler -fopenmp
-grep -A1 "k_sweepILi[0-9]*ELb1ELi1ELb0ELb0" build/fv2d_sweep_$name.ptxas.log | grep -E "Used|spill" | tr '\n' ' '; echo
+grep -A1 "k_sweepILi[0-9]*ELb1ELi1ELi0ELb0ELb1" build/fv2d_sweep_$name.ptxas.log | grep -E "Used|spill" | tr '\n' ' '; echo
