@@ -1,0 +1,80 @@
+"""Random configurations over the whole option space of the hot path, on the GPU.
+
+Same generator as tests/golden/fuzz_oracle_vs_reference.py (which pins the CPU oracle
+bit-for-bit on the reference itself, 6000 cases, dev container): here the oracle is the checker.
+  * operator-level CUDA path: bit-identical to the oracle (dt sequence, Q, U);
+  * fused sweep: within the parity bar of BASELINE.json (relative L1 <= 1e-12 on the state
+    vector, dt <= 1e-13) whenever the run is regular (finite, no negative-state resets).
+"""
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from conftest import ROOT
+from fv2d_b200 import capi
+
+sys.path.insert(0, str(ROOT / "tests" / "golden"))
+from fuzz_oracle_vs_reference import draw  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+NSTEPS = 6
+
+
+def _overrides_for_capi(ov):
+    return {k: v for k, v in ov.items()}
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+def test_random_configurations(seed):
+    rng = np.random.default_rng(seed)
+    checked = regular = 0
+    for _ in range(30):
+        base, ov = draw(rng)
+        # sizes that also span more than one strip now and then
+        if rng.random() < 0.3:
+            ov["mesh.Nx"] = int(rng.integers(250, 300))
+        try:
+            dev, run = capi.params_from_ini(str(ROOT / "settings" / base), _overrides_for_capi(ov))
+        except capi.Fv2dError:
+            continue  # configuration rejected on purpose (documented deviations)
+        Q0 = capi.init_problem(dev, run)
+        Qo = Q0.copy()
+        Uo = O.prim_to_cons(dev, Qo)
+        n, _, dts_o, neg_o = O.run(dev, run.time_stepping, run.epsilon_reset_negative, 1e30, Qo, Uo, NSTEPS)
+        # --- operator-level path: bit-identical
+        with capi.Context(dev, run.time_stepping, run.epsilon_reset_negative) as ctx:
+            ctx.upload_Q(Q0)
+            ctx.prim_to_cons()
+            dts = []
+            for _k in range(NSTEPS):
+                dt, _inv = ctx.compute_dt()
+                dts.append(dt)
+                ctx.update(dt)
+                ctx.cons_to_prim()
+                ctx.check_negatives()
+            Ug = ctx.download_U()
+        tag = f"{base} {ov}"
+        assert np.array_equal(np.array(dts), dts_o, equal_nan=True), tag
+        assert np.array_equal(O.domain(dev, Ug), O.domain(dev, Uo), equal_nan=True), tag
+        checked += 1
+        if not (np.all(np.isfinite(Uo)) and neg_o == [0, 0, 0]):
+            continue
+        # --- fused path: parity bar
+        with capi.Context(dev, run.time_stepping, run.epsilon_reset_negative) as ctx:
+            ctx.upload_Q(Q0)
+            ctx.prim_to_cons()
+            ctx.compute_dt()
+            ctx.run_steps(NSTEPS)
+            Uf = ctx.download_U()
+            fdts = ctx.dt_history(NSTEPS)
+            negf = ctx.negative_counts()
+        if negf != [0, 0, 0]:
+            continue  # a reset triggered by a rounding-level difference: not a regular run
+        assert np.max(np.abs(fdts - dts_o) / dts_o) <= 1e-13, tag
+        da, db = O.domain(dev, Uf), O.domain(dev, Uo)
+        assert float(np.sum(np.abs(da - db))) <= 1e-12 * float(np.sum(np.abs(db))), tag
+        regular += 1
+    assert checked >= 20 and regular >= 10
