@@ -81,6 +81,9 @@ __device__ __forceinline__ void tma_load_3d_u32(uint32_t dst, const CUtensorMap 
 #ifndef FV2D_PS_SHORT
 #define FV2D_PS_SHORT 1
 #endif
+#ifndef FV2D_PRODUCER_BLOCK
+#define FV2D_PRODUCER_BLOCK 1
+#endif
 #ifndef FV2D_BYTEOFF
 #define FV2D_BYTEOFF 1 // carried per-thread byte offset instead of per-row index arithmetic
 #endif
@@ -710,10 +713,22 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
     __syncthreads();
 
     // E. Q rows <= k+kDead and U rows <= k-1 are dead now: refill their slots
+#if FV2D_PRODUCER_BLOCK
+    // one block under one thread test: the other warps skip it with a single branch instead of
+    // issuing the (predicated-off) producer instructions
+    if (t == 0)
+    {
+      if (k + kDead + kNS <= rlast)
+        stage_q(k + kDead + kNS, (uint32_t)(kDead == 1 ? s1 : (kDead == 0 ? s0 : sm1)));
+      if ((k > j0) && (k - 1 + kNU < j1))
+        stage_u(k - 1 + kNU, (uint32_t)us_prev);
+    }
+#else
     if (t == 0 && k + kDead + kNS <= rlast)
       stage_q(k + kDead + kNS, (uint32_t)(kDead == 1 ? s1 : (kDead == 0 ? s0 : sm1)));
     if (t == kUProducer && (k > j0) && (k - 1 + kNU < j1))
       stage_u(k - 1 + kNU, (uint32_t)us_prev);
+#endif
 
     // D. finish row k
     {
