@@ -345,9 +345,12 @@ constexpr int kUnrollDiff = FV2D_UNROLL_DIFF;
 //   exchange arrays: X2 16 KB; X1 16 KB (PLM only: a PCM face state is the cell state, read from
 //   the Q ring itself); face sound speeds X1c 4 KB (all but PLM + HLLC); temperatures X1T 4 KB
 //   (conduction / viscosity variants)
+#ifndef FV2D_RING_CUT
+#define FV2D_RING_CUT 0 // development knob: ring slots given up (what output staging for TMA stores would cost)
+#endif
 __host__ __device__ constexpr int ring_total(bool plm, bool facec, bool diff)
 {
-  return (115712 - 256 - 16384 - (plm ? 16384 : 0) - (facec ? 4096 : 0) - (diff ? 4096 : 0)) / 8192;
+  return (115712 - 256 - 16384 - (plm ? 16384 : 0) - (facec ? 4096 : 0) - (diff ? 4096 : 0)) / 8192 - ((plm && !facec && !diff) ? FV2D_RING_CUT : 0);
 }
 // Newest Q row that no thread reads any more once the row barrier of iteration k is passed,
 // relative to k: the viscous x-face flux reads rows k-1 .. k+1 in phase B, gravity reads rho of

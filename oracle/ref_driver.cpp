@@ -11,8 +11,10 @@
 // lie under /root/reference.  Only tests/, bench.py (cpu_baseline / --impl
 // reference) and __graft_entry__.smoke() may run it.
 //
-// usage: fv2d_ref <file.ini> [--steps N] [--dump out.bin] [--load-q0 q0.bin]
-//                 [--bench] [--warmup W] [--quiet]
+// usage: fv2d_ref <file.ini> [--steps N] [--dump out.bin] [--dump-lean out.bin]
+//                 [--load-q0 q0.bin] [--bench] [--warmup W] [--quiet]
+// (--dump-lean: dt sequence, U_N and the mass/energy sums only - for the full-size grids, where
+//  three copies of the state would not fit the box)
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -66,7 +68,7 @@ int main(int argc, char **argv)
   long nsteps     = -1; // -1: run to tend like the reference
   long warmup     = 0;
   std::string dump_path, q0_path;
-  bool bench = false, quiet = false;
+  bool bench = false, quiet = false, lean = false;
   for (int a = 2; a < argc; ++a)
   {
     std::string s = argv[a];
@@ -76,6 +78,11 @@ int main(int argc, char **argv)
       warmup = std::atol(argv[++a]);
     else if (s == "--dump" && a + 1 < argc)
       dump_path = argv[++a];
+    else if (s == "--dump-lean" && a + 1 < argc)
+    {
+      dump_path = argv[++a];
+      lean      = true;
+    }
     else if (s == "--load-q0" && a + 1 < argc)
       q0_path = argv[++a];
     else if (s == "--bench")
@@ -117,7 +124,7 @@ int main(int argc, char **argv)
     primToCons(Q, U, params);
 
     std::vector<double> Q0;
-    if (!dump_path.empty())
+    if (!dump_path.empty() && !lean)
       gatherDomain(Q, device_params, Q0);
 
     if (!quiet)
@@ -163,7 +170,8 @@ int main(int argc, char **argv)
     }
 
     std::vector<double> QN, UN;
-    gatherDomain(Q, device_params, QN);
+    if (!lean)
+      gatherDomain(Q, device_params, QN);
     gatherDomain(U, device_params, UN);
     const size_t n = size_t(device_params.Nx) * device_params.Ny;
     double mass = 0.0, energy = 0.0;
@@ -187,14 +195,17 @@ int main(int argc, char **argv)
         std::fprintf(stderr, "cannot open %s\n", dump_path.c_str());
         return 4;
       }
-      const char magic[8] = {'F', 'V', '2', 'D', 'D', 'U', 'M', 'P'};
+      const char magic[8] = {'F', 'V', '2', 'D', lean ? 'L' : 'D', lean ? 'E' : 'U', lean ? 'A' : 'M', lean ? 'N' : 'P'};
       int32_t hdr[4]      = {device_params.Nx, device_params.Ny, int32_t(step), 4};
       std::fwrite(magic, 1, 8, f);
       std::fwrite(hdr, sizeof(int32_t), 4, f);
       std::fwrite(&t, sizeof(double), 1, f);
       std::fwrite(dts.data(), sizeof(double), dts.size(), f);
-      std::fwrite(Q0.data(), sizeof(double), Q0.size(), f);
-      std::fwrite(QN.data(), sizeof(double), QN.size(), f);
+      if (!lean)
+      {
+        std::fwrite(Q0.data(), sizeof(double), Q0.size(), f);
+        std::fwrite(QN.data(), sizeof(double), QN.size(), f);
+      }
       std::fwrite(UN.data(), sizeof(double), UN.size(), f);
       double sums[2] = {mass, energy};
       std::fwrite(sums, sizeof(double), 2, f);

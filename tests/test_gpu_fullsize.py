@@ -17,7 +17,7 @@ from fv2d_b200 import capi
 
 pytestmark = pytest.mark.gpu
 
-NSTEPS = 4
+NSTEPS = 10  # the bar is stated "after 10 steps"
 
 CASES = {
     # name: (settings file, overrides, conserved quantities to check {index of mass_energy(): tolerance})

@@ -1,0 +1,36 @@
+"""BASELINE.json's parity bar evaluated DIRECTLY at its full-size configurations: the fused CUDA
+path against the reference's own Kokkos-OpenMP binary (oracle/_ref/fv2d_ref, test infrastructure)
+on identical inputs, 10 steps: relative L1 <= 1e-12 on the conserved fields, dt sequence <= 1e-13,
+domain-integrated mass / energy equal to the reference's to 1e-13 (scripts/parity_fullsize.py has
+the procedure; its record of a run on the B200 box is committed under profiles/)."""
+import shutil
+import sys
+import tempfile
+
+import pytest
+
+from conftest import ROOT
+
+sys.path.insert(0, str(ROOT / "scripts"))
+import parity_fullsize as P  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", sorted(P.CASES))
+def test_fused_path_matches_the_reference_binary_at_full_size(name):
+    if not P.REF.exists():
+        pytest.skip("oracle/_ref/fv2d_ref not built (dev container: make -C oracle ref)")
+    ram, disk = P.needs(name)
+    if P.mem_available_gb() < ram or shutil.disk_usage(tempfile.gettempdir()).free / 1e9 < disk:
+        pytest.skip(f"needs {ram:.0f} GB host RAM and {disk:.0f} GB scratch")
+    rec = P.run_case(name, steps=10)
+    print(rec)
+    assert rec["negatives"] == [0, 0, 0]
+    assert rec["dt_max_rel_err"] <= P.BAR_DT, rec
+    for f in (0, 3):
+        assert rec["rel_l1"][f]["rel_l1"] <= P.BAR_L1, rec
+    for f in (1, 2):
+        assert min(rec["rel_l1"][f]["rel_l1"], rec["rel_l1"][f]["rel_l1_vs_state"]) <= P.BAR_L1, rec
+    assert rec["mass"]["rel_diff"] <= P.BAR_SUM and rec["energy"]["rel_diff"] <= P.BAR_SUM, rec
+    assert rec["pass"]
