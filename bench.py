@@ -32,6 +32,9 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 BYTES_PER_CELL_UPDATE = 128  # read Q,U + write U,Q, fp64 x 4 fields
+# fp64-pipe instructions (DFMA/DMUL/DADD/DSETP) the shipped sweep executes per cell-update, from the
+# SASS of the row loop (scripts/sass_lines.py; profiles/README.md): numerator of the fp64 roofline
+FP64_INSTR_PER_CELL_UPDATE = {"kelvin_helmholtz_8192_plm_hllc": 177, "rayleigh_taylor_16384_plm_hllc": 183}
 WORKLOADS = {
     # name: (ini, overrides)
     "kelvin_helmholtz_8192_plm_hllc": ("kelvin_helmholtz.ini", {"mesh.Nx": 8192, "mesh.Ny": 8192,
@@ -144,23 +147,24 @@ def run_reference_binary(workload: str, extra, steps: int, warmup: int):
 
 
 def reference_arm(args):
-    """--impl reference: the reference's own CPU implementation on the box's host cores."""
+    """--impl reference: the reference's own CPU implementation (oracle/_ref/fv2d_ref = the
+    unmodified reference headers + Kokkos-OpenMP) on the box's host cores, on the SAME grid as the
+    native arm.  The number of timed steps is capped so that the run ends within a few minutes
+    (one 8192^2 step is ~2.5 s of CPU time on 16 cores); throughput per step does not depend on it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    steps, warmup = min(args.steps, args.ref_max_steps), min(args.warmup, 3)
+    r = run_reference_binary(args.workload, {}, steps, warmup)
     base, ov = WORKLOADS[args.workload]
-    # bounded sample of the workload: same configuration and row length, 1/16 of the rows
-    ny = max(64, int(ov.get("mesh.Ny", 256)) // args.ref_row_fraction)
-    extra = {"mesh.Ny": ny}
-    r = run_reference_binary(args.workload, extra, args.steps, args.warmup)
-    sample = (f"{args.workload} with Ny={ny} (1/{args.ref_row_fraction} of the rows, same Nx), {r['steps']} timed steps "
-              f"after {args.warmup} warm-up, {r['cores']} OpenMP threads")
+    sample = (f"{args.workload} at its full size ({ov.get('mesh.Nx')}x{ov.get('mesh.Ny')}), {r['steps']} timed steps after "
+              f"{warmup} warm-up, {r['cores']} OpenMP threads")
     line = {
         "impl": "reference", "metric": "Mcell-updates/s", "value": r["value"], "unit": "Mcell-updates/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": warmup,
         "ms_per_step": 1e3 * r["seconds"] / max(r["steps"], 1), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "sample": sample},
+        "config": {"workload": args.workload, "Nx": ov.get("mesh.Nx"), "Ny": ov.get("mesh.Ny"), "sample": sample},
         "cpu_baseline": {"value": r["value"], "unit": "Mcell-updates/s", "cores": r["cores"], "kind": r["kind"],
                          "sample": sample},
         "e2e": {"value": r["value"], "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -170,86 +174,171 @@ def reference_arm(args):
     return 0
 
 
+class Job:
+    """One workload resident on this rank's GPU (its y-slab of the grid)."""
+
+    def __init__(self, env, workload, extra=None):
+        from fv2d_b200 import capi
+
+        self.env = env
+        base, ov = WORKLOADS[workload]
+        ov = dict(ov)
+        ov.update(extra or {})
+        self.workload = workload
+        self.dev, self.run = capi.params_from_ini(ROOT / "settings" / base, ov)
+        self.Nx, self.Ny = self.dev.Nx, self.dev.Ny
+        self.ctx = capi.Context(self.dev, self.run.time_stepping, self.run.epsilon_reset_negative, device=env.local_rank,
+                                rank=env.rank, nranks=env.world)
+        self.ctx.set_stream(env.stream.cuda_stream)
+        self.Nyl = self.ctx.Ny
+        # synthetic initial condition from the reference's own init function, on the host; each
+        # rank evaluates only the rows of its own y-slab (+ ghost rows)
+        t0 = time.perf_counter()
+        self.Qloc = capi.init_problem_rows(self.dev, self.run, self.ctx.j_offset, self.Nyl + 2 * self.dev.Ng)
+        self.host_init_s = time.perf_counter() - t0
+        if env.world > 1:
+            from fv2d_b200 import multigpu
+
+            multigpu.connect(self.ctx, env.dist)
+        self.ctx.upload_Q(self.Qloc)
+        self.ctx.prim_to_cons()
+        self.ctx.compute_dt()
+        self.ctx.sync()
+
+    def timed(self, steps):
+        """`steps` fused steps between barrier + synchronize, CUDA events on the context's stream,
+        maximum over the ranks.  Returns (ms, sweep_ms, sweep_launches, all_launches) of this region."""
+        import torch
+
+        env, ctx = self.env, self.ctx
+        ctx.profile_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        env.barrier()
+        with torch.cuda.stream(env.stream):
+            e0.record(env.stream)
+            ctx.run_steps(steps)
+            e1.record(env.stream)
+        env.barrier()
+        ms = env.max_over_ranks(e0.elapsed_time(e1))
+        sweep_ms, sweep_launches, total_launches = ctx.profile_read()
+        ctx.profile_enable(False)
+        return ms, sweep_ms, sweep_launches, total_launches
+
+    def global_hash(self):
+        """Hash of the conserved state of the WHOLE grid: slab hashes added modulo 2^64."""
+        h = self.ctx.state_hash()
+        if self.env.world > 1:
+            import torch
+
+            mine = torch.tensor([h - (1 << 64) if h >= (1 << 63) else h], dtype=torch.int64, device="cuda")
+            out = [torch.empty_like(mine) for _ in range(self.env.world)]
+            self.env.dist.all_gather(out, mine)
+            h = sum(int(t.item()) for t in out) % (1 << 64)
+        return h
+
+    def roofline(self, sweep_ms, sweep_launches, peak):
+        per_launch_s = (sweep_ms / max(sweep_launches, 1)) * 1e-3
+        achieved = BYTES_PER_CELL_UPDATE * self.Nx * self.Nyl / per_launch_s / 1e9
+        return per_launch_s, achieved, achieved / peak
+
+    def close(self):
+        self.ctx.sync()
+        self.env.barrier()
+        self.ctx.close()
+        self.Qloc = None
+
+
+class Env:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+        torch.cuda.set_device(self.local_rank)
+        self.dist = dist
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.stream = torch.cuda.Stream()
+        self.torch = torch
+        os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // self.world)))
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world > 1:
+            tmax = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+            self.dist.all_reduce(tmax, op=self.dist.ReduceOp.MAX)
+            return float(tmax.item())
+        return float(x)
+
+
+HASH_STEPS = 16  # the state hash is taken after this many steps from the initial condition, whatever --steps / --warmup
+
+
 def native_arm(args):
     import torch
-    import torch.distributed as dist
 
     from fv2d_b200 import capi
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    env = Env()
+    world, rank = env.world, env.rank
+    peak, peak_src = measured_peak_gbs()
 
-    base, ov = WORKLOADS[args.workload]
-    ov = dict(ov)
+    extra = {}
     if args.nx:
-        ov["mesh.Nx"] = args.nx
+        extra["mesh.Nx"] = args.nx
     if args.ny:
-        ov["mesh.Ny"] = args.ny
-    dev, run = capi.params_from_ini(ROOT / "settings" / base, ov)
-    Nx, Ny = dev.Nx, dev.Ny
+        extra["mesh.Ny"] = args.ny
+    job = Job(env, args.workload, extra)
+    ctx, Nx, Ny, Nyl = job.ctx, job.Nx, job.Ny, job.Nyl
 
-    ctx = capi.Context(dev, run.time_stepping, run.epsilon_reset_negative, device=local_rank, rank=rank, nranks=world)
-    stream = torch.cuda.Stream()
-    ctx.set_stream(stream.cuda_stream)
-    Nyl, joff = ctx.Ny, ctx.j_offset
-    # synthetic initial condition from the reference's own init function, on the host; each
-    # rank evaluates only the rows of its own y-slab (+ ghost rows)
-    os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
-    t_init = time.perf_counter()
-    Qloc = capi.init_problem_rows(dev, run, joff, Nyl + 2 * dev.Ng)
-    t_init = time.perf_counter() - t_init
-    if world > 1:
-        from fv2d_b200 import multigpu
-
-        multigpu.connect(ctx, dist)
-    ctx.upload_Q(Qloc)
-    ctx.prim_to_cons()
-    ctx.compute_dt()
-    ctx.sync()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    # ---- state hash after a FIXED number of steps from the initial condition: the N-GPU result
+    #      is bitwise the 1-GPU result, so this value must be the same in every --gpus N line
+    ctx.run_steps(HASH_STEPS)
+    state_hash = job.global_hash()
 
     # ---- warm-up
     ctx.run_steps(args.warmup)
-    barrier()
+    env.barrier()
 
-    # ---- timed region: K fused steps, state resident in HBM, dt resident on the device
-    sampler = ClockSampler(local_rank)
+    # ---- timed region: K fused steps, state resident in HBM, dt resident on the device;
+    #      repeated `reps` times, the MEDIAN repetition is reported (BASELINE.md section 4)
+    sampler = ClockSampler(env.local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.2)
-    ctx.profile_enable(True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        ctx.run_steps(args.steps)
-        e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    sweep_ms, sweep_launches, total_launches = ctx.profile_read()
-    ctx.profile_enable(False)
+    reps = []
+    for _ in range(max(1, args.reps)):
+        reps.append(job.timed(args.steps))
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        tmax = torch.tensor([ms], device="cuda")
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms = float(tmax.item())
+    order = sorted(range(len(reps)), key=lambda k: reps[k][0])
+    ms, sweep_ms, sweep_launches, total_launches = reps[order[len(order) // 2]]
     value = Nx * Ny * args.steps / (ms * 1e-3) / 1e6
+    per_launch_s, achieved, frac = job.roofline(sweep_ms, sweep_launches, peak)
+
+    # ---- sustained regime: one region of >= 200 back-to-back steps whatever --steps says (a short
+    #      region runs at boost clocks; a production run is thousands of steps under the power cap)
+    sustained = None
+    if args.sustained_steps > 0:
+        n_sus = max(args.sustained_steps, args.steps)
+        sampler2 = ClockSampler(env.local_rank)
+        if rank == 0:
+            sampler2.start()
+            time.sleep(0.2)
+        s_ms, s_sweep_ms, s_launches, _ = job.timed(n_sus)
+        s_clocks = sampler2.stop() if rank == 0 else None
+        s_per_launch, s_achieved, s_frac = job.roofline(s_sweep_ms, s_launches, peak)
+        sustained = {"steps": n_sus, "ms_per_step": s_ms / n_sus, "value": Nx * Ny * n_sus / (s_ms * 1e-3) / 1e6,
+                     "unit": "Mcell-updates/s", "frac": s_frac, "ms_per_launch": s_per_launch * 1e3, "clocks": s_clocks}
     neg = ctx.negative_counts()
 
-    # ---- roofline of the dominant kernel (the fused sweep), per launch, local slab
-    peak, peak_src = measured_peak_gbs()
-    per_launch_s = (sweep_ms / max(sweep_launches, 1)) * 1e-3
-    achieved = BYTES_PER_CELL_UPDATE * Nx * Nyl / per_launch_s / 1e9
     traffic = None
     tj = ROOT / "profiles" / "sweep_traffic.json"
     if tj.exists():
@@ -260,41 +349,79 @@ def native_arm(args):
         except Exception:
             pass
 
+    # ---- second roofline: the fp64 pipe.  Peak = measured DFMA rate of this device (dependent-DFMA
+    #      chains); achieved = fp64-pipe instructions the sweep executes per cell-update (counted in the
+    #      SASS of the shipped kernel, profiles/README.md) x cell-updates per second of the sweep.
+    fp64 = None
+    try:
+        peak_dfma = capi.fp64_peak(env.local_rank)
+        ach = FP64_INSTR_PER_CELL_UPDATE.get(args.workload)
+        if ach:
+            rate = ach * Nx * Nyl / per_launch_s
+            fp64 = {"peak_dfma_per_s": peak_dfma, "peak_tflops": 2 * peak_dfma / 1e12, "fp64_instr_per_cell_update": ach,
+                    "achieved_instr_per_s": rate, "frac": rate / peak_dfma,
+                    "peak_source": "measured on this device: fv2d_debug_fp64_peak (dependent DFMA chains, 8 per thread)"}
+    except Exception as e:  # noqa
+        fp64 = {"error": str(e)}
+
     # ---- end to end through the host-buffer C ABI call: every step uploads the state from
     #      pinned host memory, advances one step and reads the new state + dt back
     #      (N > 1: every rank does so for its own y-slab, ghost rows included; wall clock between
     #      two barriers, maximum over the ranks)
     e2e = None
     if args.e2e_steps > 0:
-        hin = torch.from_numpy(Qloc).pin_memory()
+        hin = torch.from_numpy(job.Qloc).pin_memory()
         hout = torch.empty_like(hin).pin_memory()
         a_in, a_out = hin.numpy(), hout.numpy()
         dts = np.zeros(1)
         ctx.advance_host(a_in, a_out, 1, dts)  # warm-up
         a_in, a_out = a_out, a_in
-        barrier()
+        env.barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             ctx.advance_host(a_in, a_out, 1, dts)
             a_in, a_out = a_out, a_in
-        barrier()
-        secs = time.perf_counter() - t0
-        if world > 1:
-            tsec = torch.tensor([secs], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
-            secs = float(tsec.item())
-        nbytes = int(Qloc.nbytes) * world
+        env.barrier()
+        secs = env.max_over_ranks(time.perf_counter() - t0)
+        nbytes = int(job.Qloc.nbytes) * world
         e2e = {"value": Nx * Ny * args.e2e_steps / secs / 1e6, "unit": "Mcell-updates/s",
                "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 8 * world, "steps": args.e2e_steps,
                "api": "fv2d_advance_host(ctx, hostQ_in, hostQ_out, 1, &dt)" + (" on every rank's y-slab" if world > 1 else "")}
+        del hin, hout, a_in, a_out
+    host_init_s, slab_gb = job.host_init_s, job.Qloc.nbytes * world / 1e9
+    job.close()
 
-    # ---- CPU baseline beside it (rank 0, N=1 only): the reference itself on a bounded sample
+    # ---- north_star's scaling targets, in every line: strong scaling of Rayleigh-Taylor 16384^2
+    #      (the same grid on N GPUs) and weak scaling of Kelvin-Helmholtz (8192 rows per GPU)
+    def side_block(workload, extra_ov, steps, scaling):
+        j = Job(env, workload, extra_ov)
+        j.ctx.run_steps(max(3, args.warmup // 2))
+        env.barrier()
+        b_ms, b_sweep_ms, b_launches, _ = j.timed(steps)
+        pl, ach, fr = j.roofline(b_sweep_ms, b_launches, peak)
+        out = {"workload": workload, "Nx": j.Nx, "Ny": j.Ny, "scaling": scaling, "steps": steps,
+               "value": j.Nx * j.Ny * steps / (b_ms * 1e-3) / 1e6, "unit": "Mcell-updates/s", "ms_per_step": b_ms / steps,
+               "frac": fr, "ms_per_launch": pl * 1e3, "state_hash": None}
+        j.close()
+        return out
+
+    strong_16384 = weak = None
+    if not args.no_scaling_blocks:
+        strong_16384 = side_block("rayleigh_taylor_16384_plm_hllc", {}, args.side_steps, "strong")
+        if world == 1 and args.workload == "kelvin_helmholtz_8192_plm_hllc" and not extra:
+            weak = {"workload": args.workload, "Nx": Nx, "Ny": Ny, "rows_per_gpu": Ny, "scaling": "weak", "steps": args.steps,
+                    "value": value, "unit": "Mcell-updates/s", "ms_per_step": ms / args.steps, "frac": frac,
+                    "ms_per_launch": per_launch_s * 1e3, "note": "N=1: the headline run itself"}
+        else:
+            weak = side_block("kelvin_helmholtz_8192_plm_hllc", {"mesh.Ny": 8192 * world}, max(args.side_steps, 40), "weak")
+            weak["rows_per_gpu"] = 8192
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the reference itself, same grid, fewer steps
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample_n = args.cpu_sample
-        r = run_reference_binary(args.workload, {"mesh.Nx": sample_n, "mesh.Ny": sample_n}, args.cpu_steps, 2)
+        r = run_reference_binary(args.workload, extra, args.cpu_steps, 1)
         cpu = {"value": r["value"], "unit": "Mcell-updates/s", "cores": r["cores"], "kind": r["kind"],
-               "sample": f"{args.workload} scaled to {sample_n}x{sample_n}, {r['steps']} timed steps after 2 warm-up "
+               "sample": f"{args.workload} at its full size ({Nx}x{Ny}), {r['steps']} timed steps after 1 warm-up "
                          f"({r['seconds']:.1f} s of CPU work)"}
 
     if rank == 0:
@@ -303,21 +430,24 @@ def native_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "Nx": Nx, "Ny": Ny, "riemann_solver": "hllc",
-                       "reconstruction": {0: "pcm", 1: "pcm_wb", 2: "plm"}[dev.reconstruction],
-                       "time_stepping": "euler" if run.time_stepping == 0 else "rk2",
+                       "reconstruction": {0: "pcm", 1: "pcm_wb", 2: "plm"}[job.dev.reconstruction],
+                       "time_stepping": "euler" if job.run.time_stepping == 0 else "rk2",
                        "decomposition": f"{world} y-slab(s)", "l2_policy": "working set (3 arrays x %.2f GB) >> 126 MB L2"
-                       % (Qloc.nbytes * world / 1e9), "host_init_s": round(t_init, 2)},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_sweep (fused RK stage)", "peak_source": peak_src,
+                       % slab_gb, "host_init_s": round(host_init_s, 2),
+                       "repetitions": len(reps), "value_is": "median repetition",
+                       "ms_per_step_all_repetitions": [r[0] / args.steps for r in reps]},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": frac,
+                         "traffic": traffic, "kernel": "k_sweep (fused RK stage, persistent)", "peak_source": peak_src,
                          "bytes_per_cell_update": BYTES_PER_CELL_UPDATE, "ms_per_launch": per_launch_s * 1e3,
-                         "share_of_step": sweep_ms / ms if ms > 0 else None},
+                         "share_of_step": sweep_ms / ms if ms > 0 else None, "fp64": fp64},
+            "sustained": sustained, "state_hash": {"after_steps": HASH_STEPS, "u64": f"0x{state_hash:016x}"},
+            "strong_16384": strong_16384, "weak": weak,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(total_launches), "clocks": clocks,
             "sanity": {"negative_density": neg[0], "negative_pressure": neg[1], "nan": neg[2]},
         }
         print(json.dumps(line), flush=True)
-    ctx.close()
     if world > 1:
-        dist.destroy_process_group()
+        env.dist.destroy_process_group()
     return 0
 
 
@@ -331,9 +461,12 @@ def main():
     ap.add_argument("--nx", type=int, default=0, help="override Nx (development only)")
     ap.add_argument("--ny", type=int, default=0, help="override Ny (development only)")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--cpu-sample", type=int, default=2048, help="edge of the CPU-baseline sample grid")
-    ap.add_argument("--cpu-steps", type=int, default=40)
-    ap.add_argument("--ref-row-fraction", type=int, default=16)
+    ap.add_argument("--reps", type=int, default=3, help="repetitions of the timed region; the median is reported")
+    ap.add_argument("--sustained-steps", type=int, default=200, help="length of the sustained-regime region (0: skip)")
+    ap.add_argument("--side-steps", type=int, default=20, help="timed steps of the strong_16384 / weak blocks")
+    ap.add_argument("--no-scaling-blocks", action="store_true", help="skip the strong_16384 / weak blocks")
+    ap.add_argument("--cpu-steps", type=int, default=6, help="timed steps of the in-line CPU baseline (full grid)")
+    ap.add_argument("--ref-max-steps", type=int, default=40, help="cap on the timed steps of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -190,6 +190,10 @@ def lib() -> C.CDLL:
         "fv2d_halo_connect": [_ctxp, C.c_char_p, C.c_int],
         "fv2d_get_inv_dt": [_ctxp, _dp],
         "fv2d_debug_math_probe": [C.c_int, C.c_int64, _dp, _dp, _dp, _dp],
+        "fv2d_state_hash": [_ctxp, C.POINTER(C.c_uint64)],
+        "fv2d_debug_fp64_peak": [C.c_int, _dp],
+        "fv2d_debug_sweep_timing": [_ctxp, C.POINTER(C.c_int64), C.c_int],
+        "fv2d_debug_schedule": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int)],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)
@@ -272,6 +276,21 @@ def math_probe(a: np.ndarray, b: np.ndarray, device: int = 0):
     r, c = np.empty_like(a), np.empty_like(a)
     _check(lib().fv2d_debug_math_probe(device, a.size, _ptr(a), _ptr(b), _ptr(r), _ptr(c)))
     return r, c
+
+
+def schedule_runs(Nx: int, Ny_local: int, num_sms: int = 148, neighbour_lo: bool = False, neighbour_hi: bool = False):
+    """Row runs [(first, last), ...] of the persistent sweep's work table (host logic, no GPU needed)."""
+    buf = (C.c_int32 * (2 * 65536))()
+    n = C.c_int()
+    _check(lib().fv2d_debug_schedule(Nx, Ny_local, num_sms, int(neighbour_lo), int(neighbour_hi), buf, 65536, C.byref(n)))
+    return [(buf[2 * k], buf[2 * k + 1]) for k in range(n.value)]
+
+
+def fp64_peak(device: int = 0) -> float:
+    """Measured fp64 peak of the device in thread-level DFMA instructions per second."""
+    r = C.c_double()
+    _check(lib().fv2d_debug_fp64_peak(device, C.byref(r)))
+    return r.value
 
 
 class Context:
@@ -413,6 +432,20 @@ class Context:
         m, e = C.c_double(), C.c_double()
         _check(lib().fv2d_integrate_mass_energy(self._h, C.byref(m), C.byref(e)))
         return m.value, e.value
+
+    def state_hash(self) -> int:
+        """Decomposition-independent 64-bit hash of the local slab's conserved state (slab hashes
+        add modulo 2**64 to the hash of the whole grid)."""
+        h = C.c_uint64()
+        _check(lib().fv2d_state_hash(self._h, C.byref(h)))
+        return int(h.value)
+
+    def sweep_timing(self, n_ctas: int) -> np.ndarray:
+        """Development hook (-DFV2D_TIMING builds): [n_ctas, 4] cycles outside / inside the row loops,
+        items, total of the last sweep."""
+        out = np.zeros((n_ctas, 4), dtype=np.int64)
+        _check(lib().fv2d_debug_sweep_timing(self._h, out.ctypes.data_as(C.POINTER(C.c_int64)), 4 * n_ctas))
+        return out
 
     def halo_export(self) -> bytes:
         buf = C.create_string_buffer(FV2D_IPC_HANDLE_BYTES)

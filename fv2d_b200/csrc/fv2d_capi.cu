@@ -148,18 +148,14 @@ static int check_supported(const fv2d_device_params &p)
   return FV2D_OK;
 }
 
+// Every host-synchronising entry point goes through here: besides the stream it checks the
+// context's fault flag, which a kernel raises when a wait on a peer GPU (halo rows, CFL mail) timed
+// out.  From then on the sweeps run with dt = NaN, so a faulted state can not be mistaken for a result.
 static int sync_ctx(fv2d_ctx *c)
 {
+  if (c->nranks > 1) // the flag can only be raised by a cross-GPU wait
+    FV2D_CUDA(cudaMemcpyAsync(&c->sc_host->fault, &c->sc->fault, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
   FV2D_CUDA(cudaStreamSynchronize(c->stream));
-  return FV2D_OK;
-}
-
-static int read_scalars(fv2d_ctx *c)
-{
-  FV2D_CUDA(cudaMemcpyAsync(c->sc_host, c->sc, offsetof(DevScalars, dt_hist), cudaMemcpyDeviceToHost, c->stream));
-  int rc = sync_ctx(c);
-  if (rc)
-    return rc;
   if (c->sc_host->fault)
   {
     set_error("a wait on a peer GPU timed out (halo rows or CFL mail never arrived)");
@@ -168,13 +164,40 @@ static int read_scalars(fv2d_ctx *c)
   return FV2D_OK;
 }
 
-// the hyperbolic maximum of the CURRENT state, reduced over all slabs (latest mail generation)
-static double current_hyp(const fv2d_ctx *c)
+static int read_scalars(fv2d_ctx *c)
 {
+  FV2D_CUDA(cudaMemcpyAsync(c->sc_host, c->sc, offsetof(DevScalars, dt_hist), cudaMemcpyDeviceToHost, c->stream));
+  return sync_ctx(c);
+}
+
+// The hyperbolic maximum of the CURRENT state, reduced over all slabs (latest mail generation).
+// Peers post their mail from their own stream: after synchronising only the local stream a slot
+// can still hold the value of two generations ago, so the scalars are re-read until every rank's
+// generation has arrived (bounded: a peer that never posts is a fault).
+static int current_hyp(fv2d_ctx *c, double *out)
+{
+  for (int tries = 0;; ++tries)
+  {
+    bool all = true;
+    for (int q = 0; q < c->nranks; ++q)
+      all = all && c->sc_host->mail_gen[q] >= c->mail_gen;
+    if (all)
+      break;
+    if (tries > 100000)
+    {
+      set_error("the CFL mail of a peer GPU never arrived");
+      return FV2D_ERR_CUDA;
+    }
+    usleep(50);
+    int rc = read_scalars(c);
+    if (rc)
+      return rc;
+  }
   double m = -1.7976931348623157e308;
   for (int q = 0; q < c->nranks; ++q)
     m = std::fmax(m, c->sc_host->mail_inv[c->mail_gen & 1][q]);
-  return m;
+  *out = m;
+  return FV2D_OK;
 }
 
 // ------------------------------------------------------------------ step drivers
@@ -221,53 +244,112 @@ static int euler_step_ops(fv2d_ctx *c, double *Q, double *Unew, double dt)
   return FV2D_OK;
 }
 
-static int choose_chunk_rows(const fv2d_ctx *c)
+// Work-item table of the persistent sweep (fv2d_sweep.cu).  The slab is cut into strips of W
+// columns and runs of rows; one item = (strip, run).  All strips share the same runs and the table
+// is ordered run by run, strips fastest, so the CTAs working at any moment cover a band of
+// neighbouring rows (halo columns are shared through L2, few DRAM pages are open).  Run heights
+// follow a guided schedule made of ROUNDS: a round is as many runs as give every CTA slot one item
+// (#slots / #strips), all of the same height = 1/C of the rows each slot still has to do, capped at
+// `hmax`, never below `hmin`.  Equal heights inside a round keep the CTAs in step (an item is bound
+// to a CTA one item ahead, so unequal neighbours in the table would not be rebalanced); halving from
+// round to round lets the last CTAs finish within a few rows of each other; tall runs while there is
+// plenty of work keep the per-item cost (one warm-up row + ~2 us) around 1 %.  With a neighbour
+// slab the runs at that edge come first and are short: their rows travel over NVLink while the rest
+// computes.
+static std::vector<std::pair<int, int>> schedule_runs(int Ny, int nstrips, int slots, bool nb_lo, bool nb_hi)
 {
-  const char *env = std::getenv("FV2D_CHUNK_ROWS");
-  if (env && std::atoi(env) > 0)
-    return std::atoi(env);
-  // Work items (strip x chunk CTAs) all cost the same, so the sweep runs in waves of
-  // (#SMs x 2 resident CTAs): pick the chunk height that best fills the last wave, weighed
-  // against the ~1.5-row warm-up every chunk pays.
-  const int Ny = c->kp.p.Ny, W = sweep_strip_width();
-  const int nstrips = (c->kp.p.Nx + W - 1) / W;
-  const int slots   = 2 * c->num_sms;
-  int best = Ny < 64 ? Ny : 64;
-  double best_eff = -1.0;
-  for (int cr = 16; cr <= 96 && cr <= Ny; ++cr)
+  auto env_int = [](const char *name, int dflt) {
+    const char *e = std::getenv(name);
+    return (e && std::atoi(e) > 0) ? std::atoi(e) : dflt;
+  };
+  const int fixed   = env_int("FV2D_CHUNK_ROWS", 0);
+  const int hmax = env_int("FV2D_SCHED_HMAX", 96), hmin = std::min(env_int("FV2D_SCHED_HMIN", 8), hmax);
+  const double C = env_int("FV2D_SCHED_C100", 220) / 100.0;
+  const int runs_per_round = std::max(1, (slots + nstrips / 2) / nstrips);
+  std::vector<std::pair<int, int>> runs;
+  int lo = 0, hi = Ny;
+  if (nb_lo && hi - lo >= 2 * hmin)
   {
-    const long long ncta = (long long)nstrips * ((Ny + cr - 1) / cr);
-    const long long waves = (ncta + slots - 1) / slots;
-    const double eff = (double)ncta / (double)(waves * slots) * (cr / (cr + 1.5));
-    if (eff > best_eff)
+    runs.emplace_back(lo, lo + hmin);
+    lo += hmin;
+  }
+  if (nb_hi && hi - lo >= 2 * hmin)
+  {
+    runs.emplace_back(hi - hmin, hi);
+    hi -= hmin;
+  }
+  while (lo < hi)
+  {
+    int h = fixed ? fixed : (int)((double)(hi - lo) * nstrips / (slots * C));
+    h     = std::max(hmin, std::min(hmax, h));
+    for (int r = 0; r < runs_per_round && lo < hi; ++r)
     {
-      best_eff = eff;
-      best     = cr;
+      int hr = h;
+      if (hi - lo - hr < hmin)
+        hr = hi - lo; // no sliver at the end
+      runs.emplace_back(lo, lo + hr);
+      lo += hr;
     }
   }
-  return best;
+  return runs;
 }
 
+static int build_work_items(fv2d_ctx *c)
+{
+  const int W = sweep_strip_width(), Ny = c->kp.p.Ny, jbeg = c->kp.p.jbeg;
+  const int nstrips = (c->kp.p.Nx + W - 1) / W;
+  const int slots   = 2 * c->num_sms;
+  const std::vector<std::pair<int, int>> runs =
+      schedule_runs(Ny, nstrips, slots, c->kp.edge_lo == EDGE_NEIGHBOUR, c->kp.edge_hi == EDGE_NEIGHBOUR);
+  std::vector<WorkItem> items;
+  items.reserve(runs.size() * nstrips + 1);
+  for (const auto &r : runs)
+    for (int s = 0; s < nstrips; ++s)
+      items.push_back(WorkItem{s, jbeg + r.first, jbeg + r.second, 0});
+  c->n_items = (int)items.size();
+  // The persistent sweep stages rows of the NEXT item while it finishes the current one and never
+  // looks further: that needs items of at least 8 rows (more than the deepest ring).  Degenerate
+  // grids / development chunk heights below that run one CTA per item instead.
+  int min_rows = Ny;
+  for (const auto &r : runs)
+    min_rows = std::min(min_rows, r.second - r.first);
+  c->persistent = min_rows >= 8;
+  c->n_ctas     = c->persistent ? std::min(c->n_items, slots) : c->n_items;
+  items.push_back(WorkItem{0, -1, -1, 0}); // end marker
+  FV2D_CUDA(cudaMalloc(&c->items_dev, items.size() * sizeof(WorkItem)));
+  FV2D_CUDA(cudaMemcpyAsync(c->items_dev, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, c->stream));
+  FV2D_CUDA(cudaStreamSynchronize(c->stream));
+  return FV2D_OK;
+}
+
+static unsigned long long pushes_per_sweep(const fv2d_ctx *c)
+{
+  // every strip pushes its Ng edge rows to each neighbour once per sweep
+  return (unsigned long long)c->kp.p.Ng * ((c->kp.p.Nx + sweep_strip_width() - 1) / sweep_strip_width());
+}
+
+static int compute_dt_now(fv2d_ctx *c);
+
 // One fused time step (Euler: 1 sweep; RK2: 2 sweeps), dt either from the host or from the
-// device-resident CFL maximum of the current state.
+// device-resident CFL maximum of the current state.  In steady state a stage is ONE launch: the
+// sweep takes its dt from the device, writes the ghost cells of its output and advances the clock.
 static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
 {
   if (!c->tmap_ok)
     return arg_fail("TMA descriptors unavailable");
-  const int cur = c->cur, nxt = cur ^ 1;
-  StepBeginArgs b;
-  b.use_device_dt = device_dt ? 1 : 0;
-  b.dt_host       = dt_host;
-  b.acc_read      = c->acc_parity;
-  b.acc_reset     = c->acc_parity ^ 1;
-  b.advance       = 1;
   if (c->nranks > 1 && !c->connected)
     return arg_fail("multi-GPU context: call fv2d_halo_connect before stepping");
-  const unsigned long long pushes_per_sweep = 2ULL * ((c->kp.p.Nx + sweep_strip_width() - 1) / sweep_strip_width());
-  b.mail_gen      = c->mail_gen;
-  b.halo_expected = c->halo_gen * pushes_per_sweep;
-  launch_step_begin(c->kp, c->Q[cur], b, c->stream);
-  c->n_launch_total++;
+  int rc;
+  if (device_dt && !c->dt_valid && (rc = compute_dt_now(c)))
+    return rc;
+  const int cur = c->cur, nxt = cur ^ 1;
+  const unsigned long long pps = pushes_per_sweep(c);
+  auto fill_ghosts = [&](double *Q) {
+    launch_fill_ghosts(c->kp, Q, c->halo_gen * pps, c->stream);
+    c->n_launch_total++;
+  };
+  if (!c->ghosts_valid || !c->fold_ok)
+    fill_ghosts(c->Q[cur]);
   auto prof_mark = [&](int which) {
     if (c->profile && c->prof_n < kProfMax)
       cudaEventRecord(c->prof_ev[2 * c->prof_n + which], c->stream);
@@ -281,21 +363,26 @@ static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
   };
 
   SweepArgs a;
-  a.kp         = c->kp;
-  a.chunk_rows = choose_chunk_rows(c);
-  a.n_strips   = 0;
-  a.acc_slot   = c->acc_parity ^ 1;
-  a.lo_rank    = (c->rank + c->nranks - 1) % c->nranks;
-  a.hi_rank    = (c->rank + 1) % c->nranks;
-  a.mail_gen   = c->mail_gen + 1; // the final stage of this step posts the next generation
+  std::memset(&a, 0, sizeof a);
+  a.kp            = c->kp;
+  a.use_device_dt = device_dt ? 1 : 0;
+  a.dt_host       = dt_host;
+  a.fold_ghosts   = c->fold_ok ? 1 : 0;
+  a.items         = c->items_dev;
+  a.n_items       = c->n_items;
+  a.n_ctas        = c->n_ctas;
+  a.persistent    = c->persistent ? 1 : 0;
+  a.lo_rank       = (c->rank + c->nranks - 1) % c->nranks;
+  a.hi_rank       = (c->rank + 1) % c->nranks;
+  a.mail_gen      = c->mail_gen; // the final stage of this step posts the next generation
   auto set_peers = [&](int qout) {
-    a.peer_lo_Qout = (c->kp.edge_lo == EDGE_NEIGHBOUR) ? c->peerQ_lo[qout] : nullptr;
-    a.peer_hi_Qout = (c->kp.edge_hi == EDGE_NEIGHBOUR) ? c->peerQ_hi[qout] : nullptr;
+    a.peer_lo_Qout  = (c->kp.edge_lo == EDGE_NEIGHBOUR) ? c->peerQ_lo[qout] : nullptr;
+    a.peer_hi_Qout  = (c->kp.edge_hi == EDGE_NEIGHBOUR) ? c->peerQ_hi[qout] : nullptr;
+    a.halo_expected = c->halo_gen * pps;
   };
   cudaError_t e;
   if (c->time_stepping == FV2D_TS_RK2)
   {
-    int rc;
     if ((rc = ensure_ustar(c)))
       return rc;
     // stage 1: U* = U + dt L(Q), Q* = consToPrim(U*)           (Update.h:204-210)
@@ -307,11 +394,9 @@ static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
     if (e != cudaSuccess)
       return cuda_fail(e, "sweep stage 1", __FILE__, __LINE__);
     c->halo_gen++;
-    // ghosts of Q*, no clock advance                              (Update.h:211 -> :179)
-    b.advance       = 0;
-    b.halo_expected = c->halo_gen * pushes_per_sweep;
-    launch_step_begin(c->kp, c->Q[nxt], b, c->stream);
-    c->n_launch_total++;
+    // ghosts of Q* (Update.h:211 -> :179): written by stage 1 itself unless the grid is degenerate
+    if (!c->fold_ok)
+      fill_ghosts(c->Q[nxt]);
     // stage 2: U = 0.5 (U0 + U* + dt L(Q*)), Q = consToPrim(U)    (Update.h:211-220, main.cpp:80-81)
     a.Uin = c->Ustar, a.Uout = c->U, a.U0 = c->U, a.Qout = c->Q[cur], a.final_stage = 1;
     set_peers(cur);
@@ -335,22 +420,25 @@ static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
   }
   c->halo_gen++;
   c->mail_gen++;
-  c->acc_parity ^= 1;
+  c->ghosts_valid = c->fold_ok;
+  c->dt_valid     = true;
   return FV2D_OK;
 }
 
-// standalone computeDt of the current state into inv_acc[acc_parity] and sc->dt
+// standalone computeDt of the current state into inv_acc[0] (the sweeps use inv_acc[1]) and sc->dt;
+// posts the next generation of the CFL mail, which is what the next device-dt step reads
 static int compute_dt_now(fv2d_ctx *c)
 {
-  unsigned long long init = FV2D_ENC_NEG_MAX;
-  FV2D_CUDA(cudaMemcpyAsync(&c->sc->inv_acc[c->acc_parity][0], &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
-  launch_compute_dt(c->kp, c->Q[c->cur], &c->sc->inv_acc[c->acc_parity][0], c->stream);
   if (c->nranks > 1 && !c->connected)
     return arg_fail("multi-GPU context: call fv2d_halo_connect before computing dt");
+  static const unsigned long long init = FV2D_ENC_NEG_MAX;
+  FV2D_CUDA(cudaMemcpyAsync(&c->sc->inv_acc[0][0], &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+  launch_compute_dt(c->kp, c->Q[c->cur], &c->sc->inv_acc[0][0], c->stream);
   c->mail_gen++;
-  launch_finalize_dt(c->kp, &c->sc->inv_acc[c->acc_parity][0], c->mail_gen, c->stream);
+  launch_finalize_dt(c->kp, &c->sc->inv_acc[0][0], c->mail_gen, c->stream);
   c->n_launch_total += 2;
   FV2D_CUDA(cudaGetLastError());
+  c->dt_valid = true;
   return FV2D_OK;
 }
 
@@ -657,6 +745,12 @@ int fv2d_ctx_create_slab(const fv2d_device_params *dev, int time_stepping, doubl
                (make_tmap(&c->tmapU, c->U, L, sweep_strip_width()) == FV2D_OK);
   if (!c->tmap_ok)
     return fail(FV2D_ERR_CUDA);
+  if ((rc = build_work_items(c)))
+    return fail(rc);
+  // The sweep writes the ghost cells of its own output when every ghost mirrors a DOMAIN cell
+  // (always, except on grids narrower than the ghost layer, where a reflecting ghost mirrors
+  // another ghost: those keep the stand-alone ghost-fill launch).
+  c->fold_ok = dev->Nx >= dev->Ng && kp.p.Ny >= dev->Ng;
 #undef FV2D_TRY
   *out = c;
   return FV2D_OK;
@@ -684,6 +778,8 @@ void fv2d_ctx_destroy(fv2d_ctx *c)
   cudaFree(c->slopesX);
   cudaFree(c->slopesY);
   cudaFree(c->gtab);
+  cudaFree(c->items_dev);
+  cudaFree(c->rowsum);
   cudaFree(c->sc);
   if (c->prof_ev)
   {
@@ -744,6 +840,7 @@ int fv2d_upload_Q(fv2d_ctx *c, const double *hostQ)
   FV2D_ENTER(c);
   if (!hostQ)
     return arg_fail("null host array");
+  c->ghosts_valid = c->dt_valid = false;
   int rc = copy_h2d(c, c->Q[c->cur], hostQ);
   return rc ? rc : sync_ctx(c);
 }
@@ -782,6 +879,7 @@ int fv2d_prim_to_cons(fv2d_ctx *c)
 int fv2d_cons_to_prim(fv2d_ctx *c)
 {
   FV2D_ENTER(c);
+  c->ghosts_valid = c->dt_valid = false; // Q is rewritten over range_tot
   launch_cons_to_prim(c->kp, c->U, c->Q[c->cur], c->stream);
   FV2D_CUDA(cudaGetLastError());
   return FV2D_OK;
@@ -789,6 +887,7 @@ int fv2d_cons_to_prim(fv2d_ctx *c)
 int fv2d_check_negatives(fv2d_ctx *c, uint64_t counts[3])
 {
   FV2D_ENTER(c);
+  c->ghosts_valid = c->dt_valid = false; // negative cells are reset in place
   int rc;
   if ((rc = read_scalars(c)))
     return rc;
@@ -805,6 +904,7 @@ int fv2d_check_negatives(fv2d_ctx *c, uint64_t counts[3])
 int fv2d_fill_boundaries(fv2d_ctx *c)
 {
   FV2D_ENTER(c);
+  c->ghosts_valid = (c->nranks == 1); // (ghost rows on a neighbour-slab side belong to the halo exchange)
   launch_fill_boundaries(c->kp, c->Q[c->cur], c->stream);
   FV2D_CUDA(cudaGetLastError());
   return FV2D_OK;
@@ -866,6 +966,7 @@ int fv2d_euler_step(fv2d_ctx *c, double dt)
 int fv2d_update(fv2d_ctx *c, double dt)
 {
   FV2D_ENTER(c);
+  c->ghosts_valid = c->dt_valid = false; // (RK2 overwrites Q with consToPrim(U*): Update.h:210)
   if (c->time_stepping == FV2D_TS_EULER)
     return euler_step_ops(c, c->Q[c->cur], c->U, dt);
   // SSP-RK2, Update.h:197-221
@@ -945,7 +1046,9 @@ int fv2d_get_time(fv2d_ctx *c, double *t, double *next_dt, int64_t *steps)
   {
     // what step_begin would compute from the current accumulator
     const fv2d_device_params &p = c->kp.p;
-    double hyp = current_hyp(c);
+    double hyp = 0.0;
+    if ((rc = current_hyp(c, &hyp)))
+      return rc;
     double tc = p.epsilon, visc = p.epsilon;
     if (p.thermal_conductivity_active)
       tc = std::fmax(2.0 * p.kappa / (p.dx * p.dx), 2.0 * p.kappa / (p.dy * p.dy));
@@ -1013,7 +1116,8 @@ int fv2d_get_inv_dt(fv2d_ctx *c, double inv_dt[3])
     return rc;
   // maxima of the CURRENT state (what the next step's dt is made of), ComputeDt.h:30-52
   const fv2d_device_params &p = c->kp.p;
-  inv_dt[0] = current_hyp(c);
+  if ((rc = current_hyp(c, &inv_dt[0])))
+    return rc;
   inv_dt[1] = p.epsilon;
   inv_dt[2] = p.epsilon;
   if (p.thermal_conductivity_active)
@@ -1025,17 +1129,96 @@ int fv2d_get_inv_dt(fv2d_ctx *c, double inv_dt[3])
 int fv2d_integrate_mass_energy(fv2d_ctx *c, double *mass, double *energy)
 {
   FV2D_ENTER(c);
-  double *rowsum = nullptr;
-  FV2D_CUDA(cudaMalloc(&rowsum, (size_t)2 * c->kp.p.Ny * sizeof(double)));
-  launch_mass_energy(c->kp, c->U, rowsum, c->stream);
+  if (!c->rowsum)
+    FV2D_CUDA(cudaMalloc(&c->rowsum, (size_t)2 * c->kp.p.Ny * sizeof(double)));
+  launch_mass_energy(c->kp, c->U, c->rowsum, c->stream);
   int rc = read_scalars(c);
-  cudaFree(rowsum);
   if (rc)
     return rc;
   if (mass)
     *mass = c->sc_host->sums[0];
   if (energy)
     *energy = c->sc_host->sums[1];
+  return FV2D_OK;
+}
+
+int fv2d_state_hash(fv2d_ctx *c, uint64_t *hash)
+{
+  FV2D_ENTER(c);
+  if (!hash)
+    return arg_fail("null output");
+  FV2D_CUDA(cudaMemsetAsync(&c->sc->hash, 0, sizeof(unsigned long long), c->stream));
+  launch_state_hash(c->kp, c->U, &c->sc->hash, c->stream);
+  int rc = read_scalars(c);
+  if (rc)
+    return rc;
+  *hash = c->sc_host->hash;
+  return FV2D_OK;
+}
+
+int fv2d_debug_schedule(int Nx, int Ny_local, int num_sms, int neighbour_lo, int neighbour_hi, int32_t *runs, int max_runs,
+                        int *n_runs)
+{
+  if (Nx < 1 || Ny_local < 1 || num_sms < 1 || !runs || !n_runs)
+    return arg_fail("fv2d_debug_schedule: bad arguments");
+  const int W = sweep_strip_width();
+  const auto r = schedule_runs(Ny_local, (Nx + W - 1) / W, 2 * num_sms, neighbour_lo != 0, neighbour_hi != 0);
+  *n_runs      = (int)r.size();
+  for (int k = 0; k < (int)r.size() && k < max_runs; ++k)
+    runs[2 * k] = r[k].first, runs[2 * k + 1] = r[k].second;
+  return FV2D_OK;
+}
+
+int fv2d_debug_sweep_timing(fv2d_ctx *c, int64_t *out, int n)
+{
+  FV2D_ENTER(c);
+  int rc = sync_ctx(c);
+  if (rc)
+    return rc;
+  rc = read_sweep_timing((long long *)out, n);
+  if (rc == 1)
+    return arg_fail("this build of the library has no sweep timing (rebuild with -DFV2D_TIMING)");
+  if (rc)
+    return cuda_fail(cudaGetLastError(), "read_sweep_timing", __FILE__, __LINE__);
+  return FV2D_OK;
+}
+
+int fv2d_debug_fp64_peak(int device, double *dfma_per_second)
+{
+  if (!dfma_per_second)
+    return arg_fail("null output");
+  FV2D_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  FV2D_CUDA(cudaGetDeviceProperties(&prop, device));
+  double *d = nullptr;
+  FV2D_CUDA(cudaMalloc(&d, sizeof(double)));
+  cudaEvent_t e0, e1;
+  FV2D_CUDA(cudaEventCreate(&e0));
+  FV2D_CUDA(cudaEventCreate(&e1));
+  const int blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) // first repetition warms up
+  {
+    cudaEventRecord(e0, nullptr);
+    launch_fp64_peak(blocks, iters, d, nullptr);
+    cudaEventRecord(e1, nullptr);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms      = 0.f;
+    if (e == cudaSuccess)
+      e = cudaEventElapsedTime(&ms, e0, e1);
+    if (e != cudaSuccess)
+    {
+      cudaFree(d);
+      return cuda_fail(e, "fp64 peak probe", __FILE__, __LINE__);
+    }
+    const double rate = 8.0 * iters * 256.0 * blocks / (ms * 1e-3); // thread-level DFMAs per second
+    if (rep > 0 && rate > best)
+      best = rate;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *dfma_per_second = best;
   return FV2D_OK;
 }
 
@@ -1106,7 +1289,11 @@ int fv2d_advance_host(fv2d_ctx *c, const double *hostQ_in, double *hostQ_out, in
   FV2D_ENTER(c);
   if (!hostQ_in || !hostQ_out)
     return arg_fail("null host array");
+  if (dts && nsteps > FV2D_DT_HISTORY)
+    return arg_fail("fv2d_advance_host: the dt sequence of more than FV2D_DT_HISTORY steps is not kept; pass dts = NULL "
+                    "or advance in shorter calls");
   int rc;
+  c->ghosts_valid = c->dt_valid = false;
   if ((rc = copy_h2d(c, c->Q[c->cur], hostQ_in)))
     return rc;
   launch_prim_to_cons(c->kp, c->Q[c->cur], c->U, c->stream);
@@ -1121,12 +1308,7 @@ int fv2d_advance_host(fv2d_ctx *c, const double *hostQ_in, double *hostQ_out, in
     // y-slab: the ghost rows of the new state are pushed by the neighbours' sweeps; wait for
     // them (and fill the x ghosts) so the array handed back is complete and can be fed to the
     // next call as it is
-    StepBeginArgs b;
-    std::memset(&b, 0, sizeof b);
-    const unsigned long long pushes_per_sweep =
-        2ULL * ((c->kp.p.Nx + sweep_strip_width() - 1) / sweep_strip_width());
-    b.halo_expected = c->halo_gen * pushes_per_sweep;
-    launch_step_begin(c->kp, c->Q[c->cur], b, c->stream);
+    launch_fill_ghosts(c->kp, c->Q[c->cur], c->halo_gen * pushes_per_sweep(c), c->stream);
     c->n_launch_total++;
   }
   if ((rc = copy_d2h(c, hostQ_out, c->Q[c->cur])))

@@ -35,6 +35,13 @@ struct Layout
 };
 
 constexpr int kMaxRanks = 8; // y-slabs per job: the GPUs of one NVSwitch box
+// One unit of work of the persistent sweep (fv2d_sweep.cu): rows [j0, j1) of strip `strip`.
+// j0 < 0 marks the end of the table (entry n_items).  16 bytes: one cp.async into the CTA's
+// shared-memory queue.
+struct WorkItem
+{
+  int strip, j0, j1, pad;
+};
 
 // What lies beyond the low-j / high-j edge of the local slab.
 enum : int
@@ -53,12 +60,15 @@ struct DevScalars
   unsigned long long neg[4];        // cumulative {rho<0, P<0, NaN, -}
   double inv_dt_last[4];            // decoded maxima behind `dt`
   double sums[2];                   // scratch for mass/energy integration
+  unsigned long long hash;          // scratch for fv2d_state_hash
   // ---- multi-GPU mailboxes: written by peers over NVLink (system-scope stores), read locally
   unsigned long long halo_cnt[2];      // ghost-row pushes received from the low-j / high-j neighbour
   unsigned long long mail_gen[kMaxRanks]; // per source rank: generation of its last CFL mail
   double mail_inv[2][kMaxRanks];       // [generation parity][source rank]: that rank's max inverse dt
   unsigned int cta_done;               // CTAs of the running sweep that have finished (local)
   unsigned int fault;                  // set if a wait on a peer timed out
+  unsigned int work_next;              // work items handed out beyond the static first one per CTA (local)
+  unsigned int pad0_;
   double dt_hist[FV2D_DT_HISTORY];  // ring of dts used
 };
 
@@ -131,6 +141,8 @@ __device__ __forceinline__ bool wait_ge_sys(const unsigned long long *p, unsigne
 {
   if (ld_acquire_sys(p) >= v)
     return true;
+  if (*(volatile unsigned int *)&sc->fault) // an earlier wait already gave up: do not spend another 20 s
+    return false;
   unsigned long long t0, t1;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   while (ld_acquire_sys(p) < v)
@@ -200,6 +212,7 @@ struct fv2d_ctx
   double *Ustar;  // RK2 stage buffer (lazy)
   double *slopesX, *slopesY; // operator-level API only (lazy)
   double *gtab;   // analytical gravity table (or nullptr)
+  double *rowsum; // scratch of fv2d_integrate_mass_energy (lazy)
   fv2d::DevScalars *sc;
   fv2d::DevScalars *sc_host; // pinned mirror for readbacks
   double *stage_host;        // pinned staging row buffer for uploads/downloads (lazy)
@@ -208,7 +221,13 @@ struct fv2d_ctx
   CUtensorMap tmapQ[2]; // TMA descriptors of Q[0], Q[1]
   CUtensorMap tmapU, tmapUstar; // ... of U and of the RK2 stage array (valid once Ustar exists)
   bool tmap_ok;
-  int acc_parity; // which inv_acc slot the NEXT sweep accumulates into
+  // persistent sweep: work-item table (device), its length, grid size
+  fv2d::WorkItem *items_dev;
+  int n_items, n_ctas;
+  bool persistent; // every item has >= 8 rows: CTAs take several (else one CTA per item)
+  bool fold_ok;      // the sweep can write the ghost cells itself (every ghost mirrors a DOMAIN cell)
+  bool ghosts_valid; // the ghosts of Q[cur] are up to date
+  bool dt_valid;     // the device-resident CFL maximum describes Q[cur]
 
   // optional profiling: CUDA event pairs around every sweep launch
   bool profile;

@@ -21,24 +21,19 @@ void launch_thermal_conduction(const KParams &kp, const double *Q, double *Unew,
 void launch_viscosity(const KParams &kp, const double *Q, double *Unew, double dt, cudaStream_t s);
 void launch_rk2_correct(const KParams &kp, const double *U0, double *Unew, cudaStream_t s);
 void launch_mass_energy(const KParams &kp, const double *U, double *rowsum, cudaStream_t s);
+void launch_state_hash(const KParams &kp, const double *U, unsigned long long *out, cudaStream_t s);
+void launch_fp64_peak(int blocks, int iters, double *out, cudaStream_t s);
 
 // ---- fused hot path (fv2d_sweep.cu)
 
-// Step prologue: ghost fill of Q (composed x/y passes) + device-side clock bookkeeping.
-struct StepBeginArgs
-{
-  int use_device_dt; // 1: dt = CFL / max(inv_acc[acc_read]); 0: dt = dt_host
-  double dt_host;
-  int acc_read;  // inv_acc slot holding the maxima of the CURRENT state
-  int acc_reset; // inv_acc slot the coming sweep accumulates into (reset here)
-  int advance;   // 1: t += dt, step++, dt history (once per time step); 0: ghost fill only
-  unsigned long long mail_gen;      // generation of the CFL mails that make up this step's dt
-  unsigned long long halo_expected; // ghost-row pushes each neighbour must have delivered by now
-};
-void launch_step_begin(const KParams &kp, double *Q, const StepBeginArgs &a, cudaStream_t s);
+// Stand-alone ghost fill of Q (composed x/y passes; waits for `halo_expected` pushed rows on a
+// neighbour-slab side).  Only needed when Q was not produced by a sweep: the sweep writes the
+// ghosts of its own output.
+void launch_fill_ghosts(const KParams &kp, double *Q, unsigned long long halo_expected, cudaStream_t s);
 
 // One fused Runge-Kutta stage:  Uout = Uin + dt*L(Qin) [ ; Uout = 0.5*(U0 + Uout) ],
-// Qout = consToPrim(Uout) [ ; checkNegatives ; inverse-dt maxima of Qout ].
+// Qout = consToPrim(Uout) incl. its ghost cells [ ; checkNegatives ; inverse-dt maxima of Qout ;
+// t += dt ].
 struct SweepArgs
 {
   KParams kp;
@@ -46,15 +41,20 @@ struct SweepArgs
   double *Uout;
   const double *U0; // RK2 stage 2: the state at the start of the step; else nullptr
   double *Qout;
-  int final_stage; // 1: checkNegatives + dt reduction of the new state
-  int acc_slot;    // inv_acc slot to atomically max into (final stage)
-  int chunk_rows;  // rows per CTA work item
-  int n_strips;
+  int final_stage;   // 1: checkNegatives + dt reduction of the new state + clock advance
+  int use_device_dt; // 1: dt = CFL / max(inverse time-steps mailed by generation `mail_gen`); 0: dt = dt_host
+  double dt_host;
+  int fold_ghosts;   // 1: the epilogue also writes the ghost cells of Qout (boundary conditions)
+  int n_ctas;        // grid size = min(n_items, resident CTA slots); = n_items when !persistent
+  int persistent;    // 1: CTAs pull further items from the device-wide counter (every item has >= 8 rows)
+  const WorkItem *items; // device table, n_items entries + the end marker
+  int n_items;
   // multi-GPU: the neighbours' copy of Qout (peer-mapped), or nullptr at a physical edge.  The
-  // stage epilogue stores its two edge rows straight into the neighbour's ghost rows.
+  // stage epilogue stores its edge rows straight into the neighbour's ghost rows.
   double *peer_lo_Qout, *peer_hi_Qout;
   int lo_rank, hi_rank;
-  unsigned long long mail_gen; // generation stamped on this sweep's CFL mail (final stage)
+  unsigned long long mail_gen;      // generation of the CFL mails this step's dt is made of; the final stage posts mail_gen + 1
+  unsigned long long halo_expected; // ghost rows each neighbour must have pushed before they are read
 };
 // tmapQ / tmapU must describe the arrays the stage READS (Qin: boxes of strip width + 4 columns;
 // Uin: boxes of strip width columns).  Returns cudaSuccess or the launch error.
@@ -62,6 +62,7 @@ cudaError_t launch_sweep(const CUtensorMap &tmapQ, const CUtensorMap &tmapU, con
 // Opt-in dynamic shared memory etc.; call once per process before the first sweep.
 cudaError_t sweep_configure();
 int sweep_strip_width();
+int read_sweep_timing(long long *host, int n); // development hook: 0 ok, 1 not compiled in, 2 CUDA error
 // Accuracy probe of the sweep's reciprocal / sound-speed primitives (device pointers).
 void launch_math_probe(long long n, const double *a, const double *b, double *out_rcp, double *out_cs, cudaStream_t s);
 

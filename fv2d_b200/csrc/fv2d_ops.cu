@@ -525,6 +525,60 @@ __global__ void k_final_sums(KParams kp, const double *__restrict__ rowsum)
   kp.sc->sums[1] = e * kp.p.dx * kp.p.dy;
 }
 
+// ------------------------------------------------------------------ state hash, fp64 peak probe
+
+// 64-bit hash of the raw bits of the conserved state of the local slab.  Every domain cell
+// contributes mix(bits(U[f]) ^ key(f, global cell index)); the contributions are added modulo
+// 2^64, so the hash does not depend on the order of the cells nor on how the grid is cut into
+// slabs: the wrapping sum of the slab hashes of an N-GPU run equals the hash of the same state on
+// one GPU.  Used by bench.py to show N-GPU == 1-GPU bitwise from the bench lines alone.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
+{
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL; // splitmix64 finaliser
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+  return z ^ (z >> 31);
+}
+__global__ void k_state_hash(KParams kp, const double *__restrict__ U, unsigned long long *out)
+{
+  const fv2d_device_params &p = kp.p;
+  const long long ncell       = (long long)p.Nx * p.Ny;
+  unsigned long long h        = 0;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (long long)gridDim.x * blockDim.x)
+  {
+    const int jl = int(c / p.Nx), i = int(c - (long long)jl * p.Nx);
+    const unsigned long long gcell = (unsigned long long)(jl + kp.j_global_offset) * (unsigned long long)p.Nx + i;
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+    {
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(U[kp.L.at(f, i + p.ibeg, jl + p.jbeg)]);
+      h += mix64(bits ^ ((4ULL * gcell + f) * 0x9e3779b97f4a7c15ULL));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    h += __shfl_xor_sync(0xffffffffu, h, o);
+  if ((threadIdx.x & 31) == 0)
+    atomicAdd(out, h);
+}
+
+// Measured fp64 peak of the device: independent chains of dependent DFMAs, enough warps to
+// cover the pipe latency.  out[0] receives a value that depends on every chain (keeps the
+// compiler honest).  The host times the launch with CUDA events.
+__global__ void k_fp64_peak(int iters, double seed, double *out)
+{
+  double a0 = seed + threadIdx.x, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0,
+         a6 = a0 + 6.0, a7 = a0 + 7.0;
+  const double m = 1.0 - 1e-9, c = 1e-9;
+  for (int k = 0; k < iters; ++k)
+  {
+    a0 = fma(a0, m, c), a1 = fma(a1, m, c), a2 = fma(a2, m, c), a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c), a5 = fma(a5, m, c), a6 = fma(a6, m, c), a7 = fma(a7, m, c);
+  }
+  const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == 123.456)
+    out[0] = r;
+}
+
 // ------------------------------------------------------------------ launchers
 
 static inline dim3 grid2d(int nx, int ny, dim3 b) { return dim3((nx + b.x - 1) / b.x, (ny + b.y - 1) / b.y); }
@@ -580,6 +634,11 @@ void launch_rk2_correct(const KParams &kp, const double *U0, double *Unew, cudaS
 {
   k_rk2_correct<<<grid2d(kp.p.Nx, kp.p.Ny, kBlk), kBlk, 0, s>>>(kp, U0, Unew);
 }
+void launch_state_hash(const KParams &kp, const double *U, unsigned long long *out, cudaStream_t s)
+{
+  k_state_hash<<<1184, 256, 0, s>>>(kp, U, out);
+}
+void launch_fp64_peak(int blocks, int iters, double *out, cudaStream_t s) { k_fp64_peak<<<blocks, 256, 0, s>>>(iters, 1.0, out); }
 void launch_mass_energy(const KParams &kp, const double *U, double *rowsum, cudaStream_t s)
 {
   k_row_sums<<<kp.p.Ny, 256, 0, s>>>(kp, U, rowsum);

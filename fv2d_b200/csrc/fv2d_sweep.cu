@@ -9,8 +9,9 @@
 // Algorithmic traffic: read Q^n + U^n, write U^{n+1} + Q^{n+1} = 128 B per cell.
 //
 // Work decomposition ("column sweep"): the domain is cut into strips of W = NT-4 columns
-// and chunks of `chunk_rows` rows; one CTA of NT threads owns one (strip, chunk).  Thread t
-// owns column i0-2+t of the strip (2 halo columns each side) and marches through the rows:
+// and runs of rows; a work item is one (strip, row run).  The kernel is persistent: at most two
+// CTAs of NT threads per SM pull work items from a device-wide queue until it is empty.  Thread t
+// owns column i0-2+t of the item's strip (2 halo columns each side) and marches through the rows:
 //   * Q rows (primitive SoA tile row + its 2-cell x halo, 4 fields) and U rows (the strip's own
 //     cells) are staged into two shared-memory rings by TMA (one cp.async.bulk.tensor.3d box per
 //     row and ring, completion on mbarriers), several rows ahead, so HBM latency is hidden
@@ -28,7 +29,10 @@
 //   * the epilogue of a row writes U^{n+1}, converts to primitives, applies the
 //     negative-density/pressure reset, accumulates the CFL maximum, writes Q^{n+1}.
 // The per-CTA CFL maximum goes to a device scalar with one atomicMax: the next dt never
-// leaves the GPU.
+// leaves the GPU.  The sweep is the ONLY launch of a stage: this step's dt is taken from the
+// device-resident CFL maxima by every CTA at its start, the ghost cells of Q^{n+1} (boundary
+// conditions, BoundaryConditions.h:82-147, or the neighbour slab's halo rows) are written by the
+// epilogue of the rows they mirror, and the clock (t += dt) is advanced by the sweep's last CTA.
 #include "fv2d_kernels.h"
 
 #include <cstring>
@@ -71,6 +75,31 @@ __device__ __forceinline__ void tma_load_3d_u32(uint32_t dst, const CUtensorMap 
                : "memory");
 }
 
+// 16-byte asynchronous copy global -> shared (a work-table entry), and its completion wait
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// orders earlier generic-proxy accesses (here: the acquire of a neighbour's halo counter) before
+// later async-proxy accesses (the TMA loads of the rows it guards)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// Source index of ghost index k for boundary type bc (domain [beg, end), N = end - beg):
+// BoundaryConditions.h:25-38 (reflecting), :53-68 (periodic), :94-95 / :124-125 (absorbing).
+__device__ __forceinline__ int bc_src(int bc, int k, int beg, int end, int N)
+{
+  switch (bc)
+  {
+  case FV2D_BC_REFLECTING:
+    return 2 * (k < beg ? beg : end) - k - 1;
+  case FV2D_BC_PERIODIC:
+    return k < beg ? k + N : k - N;
+  default:
+    return k < beg ? beg : end - 1;
+  }
+}
+
 // Development knobs for the A/B variants built by scripts/build_variant.sh (defaults = shipped).
 #ifndef FV2D_FAST_RCP
 #define FV2D_FAST_RCP 1
@@ -81,11 +110,8 @@ __device__ __forceinline__ void tma_load_3d_u32(uint32_t dst, const CUtensorMap 
 #ifndef FV2D_PS_SHORT
 #define FV2D_PS_SHORT 1
 #endif
-#ifndef FV2D_PRODUCER_BLOCK
-#define FV2D_PRODUCER_BLOCK 1
-#endif
-#ifndef FV2D_BYTEOFF
-#define FV2D_BYTEOFF 1 // carried per-thread byte offset instead of per-row index arithmetic
+#ifndef FV2D_HLLC_UNIFORM
+#define FV2D_HLLC_UNIFORM 0 // 1: select-free HLLC tail when a whole warp takes the same branch (measured slower)
 #endif
 
 // 1/a: MUFU.RCP64H seed (relative error e0 <= ~2^-18) + ONE third-order step
@@ -160,6 +186,25 @@ struct FaceFlux
   double m, n, t, e, pout;
 };
 
+// Flux of the HLLC star state on the K side (RiemannSolvers.h:85-89 + :124-127): K = the left or
+// the right face state, SK its wave speed, (uS, pS) the contact speed and pressure.  Written with
+// explicit fma / mul intrinsics so that every call site compiles to the same arithmetic.
+__device__ __forceinline__ FaceFlux hllc_star(const FaceState &K, double SK, double uS, double pS, double entho)
+{
+  const double EK = __fma_rn(__dmul_rn(0.5, K.r), __fma_rn(K.t, K.t, __dmul_rn(K.n, K.n)), __dmul_rn(K.p, entho));
+  const double d  = frcp(__dsub_rn(SK, uS));
+  const double w  = __dsub_rn(SK, K.n);
+  const double rS = __dmul_rn(__dmul_rn(K.r, w), d);
+  const double ES = __dmul_rn(__fma_rn(pS, uS, __fma_rn(w, EK, -__dmul_rn(K.p, K.n))), d);
+  FaceFlux f;
+  f.m    = __dmul_rn(rS, uS);
+  f.n    = __fma_rn(f.m, uS, pS);
+  f.t    = __dmul_rn(f.m, K.t);
+  f.e    = __dmul_rn(__dadd_rn(ES, pS), uS);
+  f.pout = pS;
+  return f;
+}
+
 // HLLC (RiemannSolvers.h:53-128), re-associated: one reciprocal for 1/(rcL+rcR), one for
 // the star state of the side that is actually taken; same branch structure:
 //   SL > 0 -> left state; else uS > 0 -> left star; else SR > 0 -> right star; else right.
@@ -200,6 +245,21 @@ __device__ __forceinline__ FaceFlux hllc_f(const FaceState &L, const FaceState &
   const bool SLpos = __double2hiint(SL) >= 0, uSpos = __double2hiint(uS) >= 0, SRpos = __double2hiint(SR) >= 0;
   const bool left = SLpos || uSpos;
   const bool star = left ? !SLpos : SRpos;
+
+#if FV2D_HLLC_UNIFORM
+  // Development variant (measured, not shipped): a select-free tail when all 32 columns of a warp
+  // take the same branch.  It removes 35 FSELs per cell-update, but the branches keep the x and the
+  // y Riemann problem of a row from being scheduled together: fixed-latency "wait" stalls 1.38 -> 2.29
+  // per issue, eligible warps 1.20 -> 0.95, the row loop 4 % slower (profiles/README.md, round 2).
+  if (__all_sync(0xffffffffu, star))
+  {
+    const unsigned ml = __ballot_sync(0xffffffffu, left);
+    if (ml == 0xffffffffu)
+      return hllc_star(L, SL, uS, pS, entho);
+    if (ml == 0u)
+      return hllc_star(R, SR, uS, pS, entho);
+  }
+#endif
 
   const double rK = left ? L.r : R.r;
   const double uK = left ? L.n : R.n;
@@ -340,8 +400,9 @@ constexpr int kUnroll = FV2D_UNROLL;
 #endif
 constexpr int kUnrollDiff = FV2D_UNROLL_DIFF;
 // ---- shared-memory budget of a variant.  Two CTAs per SM leave 113 KB each; after the exchange
-// arrays the rest is cut into 8 KB ring slots, shared between the Q ring and the U ring so that
-// both are requested about equally many rows ahead of their use.
+// arrays (and 384 B of barriers, work queue and broadcast scalars) the rest is cut into 8 KB ring
+// slots, shared between the Q ring and the U ring so that both are requested about equally many
+// rows ahead of their use.
 //   exchange arrays: X2 16 KB; X1 16 KB (PLM only: a PCM face state is the cell state, read from
 //   the Q ring itself); face sound speeds X1c 4 KB (all but PLM + HLLC); temperatures X1T 4 KB
 //   (conduction / viscosity variants)
@@ -350,7 +411,8 @@ constexpr int kUnrollDiff = FV2D_UNROLL_DIFF;
 #endif
 __host__ __device__ constexpr int ring_total(bool plm, bool facec, bool diff)
 {
-  return (115712 - 256 - 16384 - (plm ? 16384 : 0) - (facec ? 4096 : 0) - (diff ? 4096 : 0)) / 8192 - ((plm && !facec && !diff) ? FV2D_RING_CUT : 0);
+  return (115712 - 384 - 16384 - (plm ? 16384 : 0) - (facec ? 4096 : 0) - (diff ? 4096 : 0)) / 8192 -
+         ((plm && !facec && !diff) ? FV2D_RING_CUT : 0);
 }
 // Newest Q row that no thread reads any more once the row barrier of iteration k is passed,
 // relative to k: the viscous x-face flux reads rows k-1 .. k+1 in phase B, gravity reads rho of
@@ -367,6 +429,10 @@ struct dim_if
   static constexpr int value = B ? N : 1;
 };
 
+#ifdef FV2D_TIMING
+__device__ long long g_sweep_timing[4096]; // per CTA: cycles outside the row loops, inside them, items, total
+#endif
+
 template <int NT, int kNS, int kNU, bool PLM, bool FACEC, bool DIFF>
 struct SweepSmem
 {
@@ -380,14 +446,33 @@ struct SweepSmem
   double X1T[dim_if<DIFF, 2>::value][dim_if<DIFF, NT>::value];   // temperature P / rho of each column
   double2 X2a[2][NT];  // x-face flux at the LEFT face of each column: (m, n)
   double2 X2b[2][NT];  //                                              (t, e)
+  WorkItem item[2];    // the CTA's current work item (entry ci of its sequence at ci & 1) and the next one
+  WorkItem item_in;    // landing slot of the table entry after those (cp.async, thread 0)
   uint64_t full[kNS];  // TMA completion barriers, one per Q ring slot
   uint64_t ufull[kNU]; // ... one per U ring slot
+  double dt;           // this step's dt, broadcast by thread 0
+  double inv3[3];      // the three inverse time-steps behind it {hyp, tc, visc}
+  // the item after the current one as the TMA producer (thread 0) needs it: tensor-map column of its
+  // Q rows, its first and last Q row (last < first: there is no next item), its U rows
+  int nx_xq, nx_rbase, nx_rlast, nx_j0, nx_j1;
 };
 
 // GRAV: 0 = no gravity, 1 = gravity, 2 = gravity + well-balanced flux at the y boundary
 // PLAIN: the common launch - the only stage of a forward-Euler step on a slab without neighbours -
 // whose loop-invariant tests (RK2 combine, peer pushes, final_stage) are resolved at compile time
 // instead of once per row.
+//
+// Persistent: the grid is min(#work items, 2 x #SMs) CTAs.  A work item is (strip, rows j0..j1-1);
+// CTA b starts on item b and then pulls further items from a device-wide counter.  The two TMA
+// rings do not know about items: the Q rows (j0-2 .. j1+1) and U rows (j0 .. j1-1) of the CTA's
+// items form one stream each, staged kNS / kNU rows ahead of their use ACROSS item boundaries, so a
+// new item starts on rows that are already in shared memory and the pipeline is filled once per
+// CTA, not once per item.  Items shrink towards the end of the table (guided schedule, see
+// fv2d_capi.cu: build_work_items), which evens out the tail.  A CTA knows its current item and the
+// next one, no more (deeper reservations tie work to a CTA long before it can start it: measured,
+// they unbalance the tail); every item has at least 8 rows, so a stream never runs past the next
+// item.  The row loop contains no function call and no table walk: calls inside it made ptxas keep
+// the ring bookkeeping in vector registers instead of uniform ones (+70 IMAD per row, spills).
 template <int NT, bool PLM, int SOLVER, int GRAV, bool DIFF, bool PLAIN>
 __global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : (NT <= 256 ? 2 : 1)))
 k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmU,
@@ -401,52 +486,88 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
   constexpr int kUnrollV = DIFF ? kUnrollDiff : kUnroll;
   constexpr int kNS   = ring_ns(ring_total(PLM, FACEC, DIFF), kDead, DIFF);
   constexpr int kNU   = ring_total(PLM, FACEC, DIFF) - kNS;
+#if FV2D_RING_CUT == 0
   static_assert(kNS + kDead >= 4 && kNU >= 2, "ring too shallow");
-#ifndef FV2D_UPRODUCER
-#define FV2D_UPRODUCER 0 // (a second producer thread in another warp measured 0.5 % slower)
 #endif
-  constexpr int kUProducer = (NT > FV2D_UPRODUCER) ? FV2D_UPRODUCER : 0; // thread that stages the U rows
   using Smem = SweepSmem<NT, kNS, kNU, PLM, FACEC, DIFF>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem &S = *reinterpret_cast<Smem *>(smem_raw);
 
   const fv2d_device_params &p = a.kp.p;
   const Layout &L             = a.kp.L;
+  DevScalars *const sc        = a.kp.sc;
   const double *const U0      = PLAIN ? nullptr : a.U0;
   const bool final_stage      = PLAIN ? true : (a.final_stage != 0);
   double *const peer_lo       = PLAIN ? nullptr : a.peer_lo_Qout;
   double *const peer_hi       = PLAIN ? nullptr : a.peer_hi_Qout;
+  const int Ng                = p.Ng;
 
-  const int t     = threadIdx.x;
-  const int strip = blockIdx.x;
-  const int i0    = p.ibeg + strip * W; // first interior column of the strip
-  const int col   = i0 - 2 + t;         // this thread's column
-  // chunk order: when the slab has neighbours the two edge chunks are dispatched first, so
-  // their ghost-row pushes travel over NVLink while the interior chunks compute
-  int cy = blockIdx.y;
-  if ((peer_lo != nullptr || peer_hi != nullptr) && gridDim.y > 1)
-    cy = (cy == 0) ? 0 : (cy == 1 ? (int)gridDim.y - 1 : cy - 1);
-#ifdef FV2D_TEST_NOMEM
-  cy = 0;
-#endif
-  const int j0    = p.jbeg + cy * a.chunk_rows;
-  const int j1    = min(j0 + a.chunk_rows, p.jend); // rows [j0, j1) are updated
-  const int rbase = j0 - 2;                         // first Q row staged
-  const int rlast = j1 + 1;                         // last Q row staged
-  const bool interior = (t >= 2) && (t < NT - 2) && (col < p.iend);
+  const int t  = threadIdx.x;
   const int tl = (t > 0 ? t - 1 : 0), tr = (t < NT - 1 ? t + 1 : NT - 1);
   const int tu = min(max(t - 2, 0), W - 1); // this thread's column inside a U box
 
-  const double dt    = a.kp.sc->dt;
-  const double rdx   = 1.0 / p.dx;
-  const double rdy   = 1.0 / p.dy;
-  const double rdxy  = rdx + rdy;
-  const double dtdx  = dt / p.dx;
-  const double dtdy  = dt / p.dy;
-  const double gamma = p.gamma0;
-  const double gm1   = gamma - 1.0;
-  const double entho = 1.0 / gm1;
+  // ---- TMA staging (thread 0): Q rows are NT columns x 4 fields, U rows W columns x 4 fields
+  constexpr uint32_t kQRowBytes = 4u * NT * sizeof(double);
+  constexpr uint32_t kURowBytes = 4u * W * sizeof(double);
+  const uint32_t ring0  = smem_u32(&S.ring[0][0][0]);
+  const uint32_t urng0  = smem_u32(&S.uring[0][0][0]);
+  const uint32_t bar0   = smem_u32(&S.full[0]);
+  const uint32_t ubar0  = smem_u32(&S.ufull[0]);
+  const int tma_x0      = L.lead + p.ibeg; // tensor-map column of the first domain cell
+  auto stage_q = [&](int x, int r, uint32_t slot) {
+    mbar_expect_tx_u32(bar0 + 8u * slot, kQRowBytes);
+    tma_load_3d_u32(ring0 + kQRowBytes * slot, &tmQ, x, r, 0, bar0 + 8u * slot);
+  };
+  auto stage_u = [&](int x, int r, uint32_t slot) {
+    mbar_expect_tx_u32(ubar0 + 8u * slot, kURowBytes);
+    tma_load_3d_u32(urng0 + kQRowBytes * slot, &tmU, x, r, 0, ubar0 + 8u * slot);
+  };
 
+  // ---- work queue (thread 0).  A CTA always knows its current item and the next one (the rows of
+  // the next item are staged while the current one finishes).  The item after those is taken from
+  // the device-wide counter as LATE as possible - 8 rows before the current item ends - because an
+  // item is bound to the CTA from that moment on, and work bound early cannot be rebalanced at the
+  // tail.  Nobody waits for the atomic or for the table read that follows it 5 rows later (cp.async
+  // into shared memory): both have landed when the item ends.
+  unsigned pend = 0; // requested table index (thread 0)
+  // ghost rows owned by a neighbour slab: its sweep of the previous stage pushed them (plain stores
+  // over NVLink); wait for all of them, then order those writes before the async-proxy reads of TMA
+  auto wait_halo_row = [&](int r) {
+    if constexpr (!PLAIN)
+    {
+      const int side = (r < p.jbeg) ? 0 : 1;
+      if ((r < p.jbeg || r >= p.jend) && (side == 0 ? a.kp.edge_lo : a.kp.edge_hi) == EDGE_NEIGHBOUR)
+      {
+        wait_ge_sys(&sc->halo_cnt[side], a.halo_expected, sc);
+        fence_proxy_async();
+      }
+    }
+  };
+  // Q row `off` (>= 1) rows beyond the last Q row of the current item = row off-1 of the next item
+  auto stage_q_next = [&](int off, uint32_t slot) {
+    const int r = S.nx_rbase + off - 1;
+    if (r <= S.nx_rlast)
+    {
+      wait_halo_row(r);
+      stage_q(S.nx_xq, r, slot);
+    }
+  };
+  // U row `off` (>= 0) rows beyond the last U row of the current item
+  auto stage_u_next = [&](int off, uint32_t slot) {
+    const int r = S.nx_j0 + off;
+    if (r < S.nx_j1)
+      stage_u(S.nx_xq + 2, r, slot);
+  };
+  auto publish_next = [&](const WorkItem &e) { // thread 0: e is the item after the current one
+    S.nx_xq    = tma_x0 + e.strip * W - 2;
+    S.nx_rbase = e.j0 - 2;
+    S.nx_rlast = (e.j0 < 0) ? e.j0 - 3 : e.j1 + 1;
+    S.nx_j0    = e.j0;
+    S.nx_j1    = e.j1;
+  };
+
+  // ---- kernel prologue (thread 0): barriers, the first three work items, the initial fill of both
+  // rings, and this step's dt
   if (t == 0)
   {
 #pragma unroll
@@ -457,40 +578,62 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
       mbar_init(&S.ufull[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // the first item is static (CTA b starts on item b), the second comes from the counter; with
+    // a.persistent == 0 (degenerate grids: items of fewer than 8 rows) every CTA has just its one item
+    const WorkItem e0 = a.items[blockIdx.x];
+    unsigned i1       = (unsigned)a.n_items;
+    if (a.persistent)
+      i1 = min(gridDim.x + atomicAdd(&sc->work_next, 1u), (unsigned)a.n_items);
+    S.item_in = WorkItem{0, -1, -1, 0};
+    const WorkItem e1 = a.items[i1]; // items[n_items] is the end marker
+    S.item[0] = e0, S.item[1] = e1;
+    publish_next(e1);
+    // initial fill of both rings from the first item (>= 8 rows unless it is the CTA's only one)
+    {
+      const int x = tma_x0 + e0.strip * W - 2;
+#pragma unroll 1
+      for (int n = 0; n < kNS && n < e0.j1 - e0.j0 + 4; ++n)
+      {
+        wait_halo_row(e0.j0 - 2 + n);
+        stage_q(x, e0.j0 - 2 + n, (uint32_t)n);
+      }
+#pragma unroll 1
+      for (int n = 0; n < kNU && n < e0.j1 - e0.j0; ++n)
+        stage_u(x + 2, e0.j0 + n, (uint32_t)n);
+    }
+    // dt = CFL / max(inverse time-steps of the current state)   (ComputeDt.h:64): the hyperbolic
+    // maximum was mailed to every rank by the last CTA of the previous final-stage sweep
+    double dt = a.dt_host, hyp = 0.0, tc = p.epsilon, visc = p.epsilon;
+    if (a.use_device_dt)
+    {
+      hyp = collect_cfl_mail(a.kp, a.mail_gen);
+      if (p.thermal_conductivity_active)
+        tc = fmax(2.0 * p.kappa / (p.dx * p.dx), 2.0 * p.kappa / (p.dy * p.dy));
+      if (p.viscosity_active)
+        visc = fmax(2.0 * p.mu / (p.dx * p.dx), 2.0 * p.mu / (p.dy * p.dy));
+      double m = hyp;
+      if (m < tc)
+        m = tc;
+      if (m < visc)
+        m = visc;
+      dt = p.CFL / m;
+      if (sc->fault) // a wait on a peer timed out: stop advancing (the host reports the fault)
+        dt = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    S.dt      = dt;
+    S.inv3[0] = hyp, S.inv3[1] = tc, S.inv3[2] = visc;
   }
   __syncthreads();
 
-  // The producer (thread 0) stages Q rows (NT columns x 4 fields, rows rbase .. rlast) and U rows
-  // (W columns x 4 fields, rows j0 .. j1-1) into two independent rings.
-  constexpr uint32_t kQRowBytes = 4u * NT * sizeof(double);
-  constexpr uint32_t kURowBytes = 4u * W * sizeof(double);
-  const int tma_xq     = L.lead + i0 - 2;
-  const int tma_xu     = L.lead + i0;
-  const uint32_t ring0 = smem_u32(&S.ring[0][0][0]);
-  const uint32_t urng0 = smem_u32(&S.uring[0][0][0]);
-  const uint32_t bar0  = smem_u32(&S.full[0]);
-  const uint32_t ubar0 = smem_u32(&S.ufull[0]);
-  auto stage_q = [&](int r, uint32_t slot) {
-    mbar_expect_tx_u32(bar0 + 8u * slot, kQRowBytes);
-    tma_load_3d_u32(ring0 + kQRowBytes * slot, &tmQ, tma_xq, r, 0, bar0 + 8u * slot);
-  };
-  auto stage_u = [&](int r, uint32_t slot) {
-    mbar_expect_tx_u32(ubar0 + 8u * slot, kURowBytes);
-    tma_load_3d_u32(urng0 + kQRowBytes * slot, &tmU, tma_xu, r, 0, ubar0 + 8u * slot);
-  };
-  if (t == 0)
-  {
-    for (int r = rbase; r <= min(rlast, rbase + kNS - 1); ++r)
-      stage_q(r, (uint32_t)(r - rbase));
-    for (int r = j0; r <= min(j1 - 1, j0 + kNU - 1); ++r)
-      stage_u(r, (uint32_t)(r - j0));
-  }
-
-  // ---- pre-prologue: rows j0-2, j0-1, j0 of this column (ring slots 0, 1, 2; first phase)
-  double qn[4]; // q(row k+1)
-  FaceState yp; // +y face state of row k (frame of the y normal: n = v, t = u)
-  double dyl[4]; // q(k+1) - q(k): the lower y difference of row k+1's slope, carried row to row
-  double Tk = 0.0; // temperature P / rho of (col, k) (conduction)
+  const double dt    = S.dt;
+  const double rdx   = 1.0 / p.dx;
+  const double rdy   = 1.0 / p.dy;
+  const double rdxy  = rdx + rdy;
+  const double dtdx  = dt / p.dx;
+  const double dtdy  = dt / p.dy;
+  const double gamma = p.gamma0;
+  const double gm1   = gamma - 1.0;
+  const double entho = 1.0 / gm1;
   // conduction / viscosity, done face by face and folded into the Riemann fluxes: the reference's
   //   U += dt (vf_x + vf_y)                    (Viscosity.h:112-116, not divided by the cell size: Q8)
   //   U[IE] += dt/dx (FR - FL) + dt/dy (FD - FU)               (ThermalConduction.h:106)
@@ -500,500 +643,669 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
   const bool tc_on = DIFF && p.thermal_conductivity_active, visc_on = DIFF && p.viscosity_active;
   const double mudx = visc_on ? p.mu * p.dx : 0.0, mudy = visc_on ? p.mu * p.dy : 0.0;
   const double kaprdx = tc_on ? p.kappa * rdx : 0.0, kaprdy = tc_on ? p.kappa * rdy : 0.0;
-  mbar_wait(&S.full[0], 0);
-  mbar_wait(&S.full[1], 0);
-  mbar_wait(&S.full[2], 0);
-  {
-    double qa[4], qk[4];
-#pragma unroll
-    for (int f = 0; f < 4; ++f)
-    {
-      qa[f] = S.ring[0][f][t];
-      qk[f] = S.ring[1][f][t];
-      qn[f] = S.ring[2][f][t];
-    }
-    double s[4] = {0.0, 0.0, 0.0, 0.0};
-    if constexpr (PLM)
-    {
-#pragma unroll
-      for (int f = 0; f < 4; ++f)
-        s[f] = minmod_f(qk[f] - qa[f], qn[f] - qk[f]);
-    }
-    yp.r = fma(0.5, s[0], qk[0]);
-    yp.t = fma(0.5, s[1], qk[1]);
-    yp.n = fma(0.5, s[2], qk[2]);
-    yp.p = fma(0.5, s[3], qk[3]);
-    yp.c = FACEC ? csound(gamma * yp.p, yp.r) : 0.0;
-#pragma unroll
-    for (int f = 0; f < 4; ++f)
-      dyl[f] = qn[f] - qk[f];
-    if constexpr (DIFF)
-      Tk = qk[3] * frcp(qk[0]);
-  }
-
-  FaceFlux fy_lo;  // y-face flux below row k (becomes the low face of the next row)
-  FaceState xm;    // -x face state of row k (own cell, left face), frame of the x normal
-  fy_lo.m = fy_lo.n = fy_lo.t = fy_lo.e = fy_lo.pout = 0.0;
-  xm.r = xm.n = xm.t = xm.p = xm.c = 0.0;
-
-  const long long ocol = L.at(0, col, 0);
-#if FV2D_BYTEOFF
-  // Global addresses = uniform per-(array, field) base + one per-thread byte offset that is
-  // carried and bumped by a row pitch per iteration (two integer instructions per address).
   const long long pitchB = (long long)L.pitch * (long long)sizeof(double);
   const long long planeB = L.plane * (long long)sizeof(double);
-  long long offB         = (ocol + (long long)(j0 - 1) * L.pitch) * (long long)sizeof(double); // row k
-#endif
+  const bool fold   = a.fold_ghosts != 0;
 
   double inv_dt_max = -1.7976931348623157e308;
-
-  // uniform ring bookkeeping, carried instead of recomputed from k
-  int s2 = 3 % kNS;             // ring slot of Q row k+2
-  uint32_t ph2 = (3 / kNS) & 1; // phase parity of that slot's barrier
-  int s1 = 2, s0 = 1, sm1 = 0;  // ring slots of Q rows k+1, k, k-1
-  int us = kNU - 1;             // U ring slot of row k (row j0 <-> slot 0)
-  uint32_t uph = 1;             // phase parity of that slot's barrier (flips to 0 on entering row j0)
-  // (the producer needs no counters of its own: Q row k+kDead+NS goes into the slot of row k+kDead,
-  //  U row k-1+NU into the slot of row k-1)
-  int us_prev = 0; // U ring slot of row k-1
-  if constexpr (kDead >= 0)
-  {
-    // the rows only the pre-prologue needed (rbase .. rbase+kDead) are dead once every thread has
-    // read its column: recycle their slots before the march starts
-    __syncthreads();
-    if (t == 0)
-    {
-#pragma unroll
-      for (int n = 0; n <= kDead; ++n)
-        if (rbase + kNS + n <= rlast)
-          stage_q(rbase + kNS + n, (uint32_t)n);
-    }
-  }
-
-  // ---- march: iteration k finishes row k; k = j0-1 is the warm-up (no update)
-#pragma unroll kUnrollV
-  for (int k = j0 - 1; k < j1; ++k)
-  {
-    const int par = k & 1;
-    // A. new row k+2 enters; y slopes / face states of row k+1; y-face flux at k+1/2
-    mbar_wait(&S.full[s2], ph2);
-    double qnn[4];
-#pragma unroll
-    for (int f = 0; f < 4; ++f)
-      qnn[f] = S.ring[s2][f][t];
-
-    FaceState ym, yp1;
-    {
-      double s[4] = {0.0, 0.0, 0.0, 0.0};
-      if constexpr (PLM)
-      {
-#pragma unroll
-        for (int f = 0; f < 4; ++f)
-        {
-          const double dup = qnn[f] - qn[f]; // also the lower difference of the next row
-          s[f]             = minmod_f(dyl[f], dup);
-          dyl[f]           = dup;
-        }
-      }
-      ym.r  = fma(-0.5, s[0], qn[0]);
-      ym.t  = fma(-0.5, s[1], qn[1]);
-      ym.n  = fma(-0.5, s[2], qn[2]);
-      ym.p  = fma(-0.5, s[3], qn[3]);
-      yp1.r = fma(0.5, s[0], qn[0]);
-      yp1.t = fma(0.5, s[1], qn[1]);
-      yp1.n = fma(0.5, s[2], qn[2]);
-      yp1.p = fma(0.5, s[3], qn[3]);
-      if constexpr (!FACEC)
-        ym.c = yp1.c = 0.0;
-      else if constexpr (PLM)
-      {
-        ym.c  = csound(gamma * ym.p, ym.r);
-        yp1.c = csound(gamma * yp1.p, yp1.r);
-      }
-      else
-      {
-        ym.c  = csound(gamma * ym.p, ym.r);
-        yp1.c = ym.c;
-      }
-    }
-    const double gdy = p.gy * p.dy, gdx = p.gx * p.dx;
-    FaceFlux fy_hi = riemann_f<SOLVER, FACEC>(yp, ym, entho, gamma, gdy, p.fslp_K);
-    // diffusive flux through the same face (between rows k and k+1), to be subtracted
-    double dy_t = 0.0, dy_n = 0.0, dy_e = 0.0, Tn = 0.0;
-    if constexpr (DIFF)
-    {
-      Tn   = qn[3] * frcp(qn[0]);
-      dy_e = kaprdy * (Tn - Tk); // FD of row k = FU of row k+1 (ThermalConduction.h:66-67)
-      {
-        const double u_lo = S.ring[s0][1][t], v_lo = S.ring[s0][2][t];
-        const ViscFlux vf = visc_face(qn[2], v_lo, qn[1], u_lo,                                        //
-                                      S.ring[s1][2][tr], S.ring[s1][2][tl], S.ring[s0][2][tr], S.ring[s0][2][tl], //
-                                      S.ring[s1][1][tr], S.ring[s1][1][tl], S.ring[s0][1][tr], S.ring[s0][1][tl], //
-                                      rdy, rdx);
-        dy_n = mudy * vf.n;
-        dy_t = mudy * vf.t;
-        dy_e = fma(mudy, vf.e, dy_e);
-      }
-    }
-
-    // B. x-face flux at the left face of (col, k): left state from the neighbour thread
-    //    (also runs, on don't-care data, in the warm-up iteration: no branch, so the x and y
-    //    Riemann problems of a row can be scheduled together)
-    {
-      FaceState xl;
-      if constexpr (PLM)
-      {
-        const double2 la = S.X1a[par][tl], lb = S.X1b[par][tl];
-        xl.r = la.x, xl.n = la.y, xl.t = lb.x, xl.p = lb.y;
-      }
-      else // PCM: the +x face state of the left neighbour is its cell state, still in the ring
-        xl.r = S.ring[s0][0][tl], xl.n = S.ring[s0][1][tl], xl.t = S.ring[s0][2][tl], xl.p = S.ring[s0][3][tl];
-      if constexpr (FACEC)
-        xl.c = S.X1c[par][tl];
-      else
-        xl.c = 0.0;
-      FaceFlux fx = riemann_f<SOLVER, FACEC>(xl, xm, entho, gamma, gdx, p.fslp_K);
-      if constexpr (DIFF)
-      {
-        // diffusive flux through the left x-face of (col, k): cells (col-1, k) and (col, k)
-        fx.e -= kaprdx * (Tk - S.X1T[par][tl]); // FL (ThermalConduction.h:64)
-        {
-          const ViscFlux vf = visc_face(S.ring[s0][1][t], S.ring[s0][1][tl], S.ring[s0][2][t], S.ring[s0][2][tl],          //
-                                        S.ring[s1][1][t], S.ring[sm1][1][t], S.ring[s1][1][tl], S.ring[sm1][1][tl], //
-                                        S.ring[s1][2][t], S.ring[sm1][2][t], S.ring[s1][2][tl], S.ring[sm1][2][tl], //
-                                        rdx, rdy);
-          fx.n = fma(-mudx, vf.n, fx.n);
-          fx.t = fma(-mudx, vf.t, fx.t);
-          fx.e = fma(-mudx, vf.e, fx.e);
-        }
-      }
-      S.X2a[par][t] = make_double2(fx.m, fx.n);
-      S.X2b[par][t] = make_double2(fx.t, fx.e);
-    }
-
-    // C. x slopes / face states of row k+1 (published for the neighbour on the right)
-    FaceState xm1;
-    {
-      double s[4] = {0.0, 0.0, 0.0, 0.0};
-      if constexpr (PLM)
-      {
-#pragma unroll
-        for (int f = 0; f < 4; ++f)
-          s[f] = minmod_f(qn[f] - S.ring[s1][f][tl], S.ring[s1][f][tr] - qn[f]);
-      }
-      xm1.r = fma(-0.5, s[0], qn[0]);
-      xm1.n = fma(-0.5, s[1], qn[1]);
-      xm1.t = fma(-0.5, s[2], qn[2]);
-      xm1.p = fma(-0.5, s[3], qn[3]);
-      FaceState xp1;
-      xp1.r = fma(0.5, s[0], qn[0]);
-      xp1.n = fma(0.5, s[1], qn[1]);
-      xp1.t = fma(0.5, s[2], qn[2]);
-      xp1.p = fma(0.5, s[3], qn[3]);
-      if constexpr (!FACEC)
-        xm1.c = xp1.c = 0.0;
-      else if constexpr (PLM)
-      {
-        xm1.c = csound(gamma * xm1.p, xm1.r);
-        xp1.c = csound(gamma * xp1.p, xp1.r);
-      }
-      else
-      {
-        xm1.c = ym.c; // PCM: one sound speed per cell
-        xp1.c = ym.c;
-      }
-      if constexpr (PLM)
-      {
-        S.X1a[par ^ 1][t] = make_double2(xp1.r, xp1.n);
-        S.X1b[par ^ 1][t] = make_double2(xp1.t, xp1.p);
-      }
-      if constexpr (FACEC)
-        S.X1c[par ^ 1][t] = xp1.c;
-      if constexpr (DIFF)
-        S.X1T[par ^ 1][t] = Tn;
-    }
-
-    __syncthreads();
-
-    // E. Q rows <= k+kDead and U rows <= k-1 are dead now: refill their slots
-#if FV2D_PRODUCER_BLOCK
-    // one block under one thread test: the other warps skip it with a single branch instead of
-    // issuing the (predicated-off) producer instructions
-    if (t == 0)
-    {
-      if (k + kDead + kNS <= rlast)
-        stage_q(k + kDead + kNS, (uint32_t)(kDead == 1 ? s1 : (kDead == 0 ? s0 : sm1)));
-      if ((k > j0) && (k - 1 + kNU < j1))
-        stage_u(k - 1 + kNU, (uint32_t)us_prev);
-    }
-#else
-    if (t == 0 && k + kDead + kNS <= rlast)
-      stage_q(k + kDead + kNS, (uint32_t)(kDead == 1 ? s1 : (kDead == 0 ? s0 : sm1)));
-    if (t == kUProducer && (k > j0) && (k - 1 + kNU < j1))
-      stage_u(k - 1 + kNU, (uint32_t)us_prev);
+#ifdef FV2D_TIMING
+  long long tm_mark = clock64(), tm_gap = 0, tm_loop = 0, tm_items = 0;
+  const long long tm_start = tm_mark;
 #endif
 
-    // D. finish row k
-    {
-      FaceFlux fxr, fxl;
-      {
-        const double2 ra = S.X2a[par][tr], rb = S.X2b[par][tr];
-        const double2 oa = S.X2a[par][t], ob = S.X2b[par][t];
-        fxr.m = ra.x, fxr.n = ra.y, fxr.t = rb.x, fxr.e = rb.y;
-        fxl.m = oa.x, fxl.n = oa.y, fxl.t = ob.x, fxl.e = ob.y;
-      }
-      // U^n of the own cell, staged by TMA two rows ago (the slot holds garbage in the warm-up
-      // iteration and for the halo threads: neither stores anything)
-      double un[4];
-      if (k >= j0)
-        mbar_wait(&S.ufull[us], uph);
-      {
-        const double *ub = &S.uring[us][0][0];
-#pragma unroll
-        for (int f = 0; f < 4; ++f)
-          un[f] = ub[f * W + tu];
-      }
-
-      // y fluxes back in the grid frame: (m, t, n, e) -> (rho, rho u, rho v, E)
-      // (fy_lo already holds hyperbolic minus diffusive flux of the face below; same for fy_hi now)
-      double fyl[4] = {fy_lo.m, fy_lo.t, fy_lo.n, fy_lo.e};
-      double fyh[4] = {fy_hi.m, fy_hi.t - dy_t, fy_hi.n - dy_n, fy_hi.e - dy_e};
-
-      double gyv = 0.0, gxv = 0.0, rho_k = 0.0;
-      if constexpr (GRAV != 0)
-      {
-        rho_k = S.ring[s0][0][t];
-        // getGravity (Gravity.h:39-57); GRAV == 2 also covers "well-balanced flux, no gravity" (g = 0)
-        if (p.gravity_mode == FV2D_GRAV_CONSTANT)
-          gxv = p.gx, gyv = p.gy;
-        else if (p.gravity_mode == FV2D_GRAV_ANALYTICAL)
-          gxv = gyv = a.kp.gtab[k];
-      }
-
-      double u4[4];
-      u4[0] = un[0] + (fxl.m - fxr.m) * dtdx + (fyl[0] - fyh[0]) * dtdy;
-      u4[1] = un[1] + (fxl.n - fxr.n) * dtdx + (fyl[1] - fyh[1]) * dtdy;
-      u4[2] = un[2] + (fxl.t - fxr.t) * dtdx + (fyl[2] - fyh[2]) * dtdy;
-      u4[3] = un[3] + (fxl.e - fxr.e) * dtdx + (fyl[3] - fyh[3]) * dtdy;
-      if constexpr (GRAV != 0)
-      {
-        // Update.h:161-166: both sweeps add into IV (Q4)
-        u4[2] += dt * rho_k * gxv + dt * rho_k * gyv;
-        u4[3] += dt * 0.5 * (fxl.m + fxr.m) * gxv + dt * 0.5 * (fyl[0] + fyh[0]) * gyv;
-      }
-
-      if constexpr (GRAV == 2)
-      {
-        // well-balanced flux at the global y boundary (Update.h:148-156): replaces the HYPERBOLIC
-        // flux of that face by {0, 0, pout -+ rho g dy, 0}; the diffusive part of the face stays.
-        // Applied as an in-place correction on the two rows it concerns (for the low face the
-        // roll below already dropped the hyperbolic part of the carried flux).
-        if (k == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL)
-          u4[2] += dtdy * (fy_hi.pout - rho_k * gyv * p.dy);
-        else if (k == p.jend - 1 && a.kp.edge_hi == EDGE_PHYSICAL)
-        {
-          u4[0] += dtdy * fy_hi.m;
-          u4[1] += dtdy * fy_hi.t;
-          u4[2] += dtdy * (fy_hi.n - (fy_lo.pout + rho_k * gyv * p.dy));
-          u4[3] += dtdy * fy_hi.e - dt * 0.5 * fy_hi.m * gyv;
-        }
-      }
-
-      if constexpr (DIFF)
-      {
-        // ThermalConduction.h:77-103: with a temperature boundary condition the reference replaces
-        // the cell's own x-flux FL (at jbeg) / FR (at jend-1) by a y-boundary expression (Q7a) -
-        // for that cell only, not for the neighbour sharing the face.  Reproduced as a correction
-        // to the face-based flux on those two rows.
-        const bool row_lo = (k == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL && p.bctc_ymin != FV2D_BCTC_NONE);
-        const bool row_hi = (k == p.jend - 1 && a.kp.edge_hi == EDGE_PHYSICAL && p.bctc_ymax != FV2D_BCTC_NONE);
-        if (tc_on && (row_lo || row_hi))
-        {
-          const double TC = S.ring[s0][3][t] * frcp(S.ring[s0][0][t]);
-          const double TL = S.ring[s0][3][tl] * frcp(S.ring[s0][0][tl]);
-          const double TR = S.ring[s0][3][tr] * frcp(S.ring[s0][0][tr]);
-          const double kap = p.kappa;
-          if (row_lo)
-          {
-            const double FL = kap * (TC - TL) * rdx;
-            const double FLb =
-                (p.bctc_ymin == FV2D_BCTC_FIXED_TEMPERATURE) ? kap * 2.0 * (TC - p.bctc_ymin_value) * rdy : kap * p.bctc_ymin_value;
-            u4[3] += dtdx * (FL - FLb);
-          }
-          if (row_hi)
-          {
-            const double FR = kap * (TR - TC) * rdx;
-            const double FRb =
-                (p.bctc_ymax == FV2D_BCTC_FIXED_TEMPERATURE) ? kap * 2.0 * (p.bctc_ymax_value - TC) * rdy : kap * p.bctc_ymax_value;
-            u4[3] += dtdx * (FRb - FR);
-          }
-        }
-      }
-
-#ifdef FV2D_TEST_NOMEM
-      if (interior && k >= j0 && u4[0] == 1.2345e300)
-#else
-      if (interior && k >= j0)
-#endif
-      {
-#if FV2D_BYTEOFF
-#define FV2D_AT(base, f) (*reinterpret_cast<double *>(reinterpret_cast<char *>(base) + (f) * planeB + offB))
-#define FV2D_CAT(base, f) (*reinterpret_cast<const double *>(reinterpret_cast<const char *>(base) + (f) * planeB + offB))
-#else
-        const long long o = ocol + (long long)k * L.pitch;
-#define FV2D_AT(base, f) ((base)[o + (f) * L.plane])
-#define FV2D_CAT(base, f) ((base)[o + (f) * L.plane])
-#endif
-        if (U0 != nullptr) // SSP-RK2 combine (Update.h:214-220)
-        {
-#pragma unroll
-          for (int f = 0; f < 4; ++f)
-            u4[f] = 0.5 * (FV2D_CAT(U0, f) + u4[f]);
-        }
-#pragma unroll
-        for (int f = 0; f < 4; ++f)
-          FV2D_AT(a.Uout, f) = u4[f];
-
-        // consToPrim (States.h:32-43)
-        const double ir = frcp(u4[0]);
-        double qo[4];
-        qo[0] = u4[0];
-        qo[1] = u4[1] * ir;
-        qo[2] = u4[2] * ir;
-        qo[3] = fma(-0.5, fma(u4[2], qo[2], u4[1] * qo[1]), u4[3]) * gm1; // E - (rho u . u) / 2
-        if (final_stage)
-        {
-          // checkNegatives (SimInfo.h:612-633): counted straight into the device counters on
-          // the (rare) event instead of carrying three counters through the sweep; one integer
-          // test of the two sign bits guards both comparisons
-          if ((__double2hiint(qo[0]) | __double2hiint(qo[3])) < 0)
-          {
-            if (qo[0] < 0.0)
-            {
-              qo[0] = a.kp.eps_reset;
-              atomicAdd(&a.kp.sc->neg[0], 1ULL);
-            }
-            if (qo[3] < 0.0)
-            {
-              qo[3] = a.kp.eps_reset;
-              atomicAdd(&a.kp.sc->neg[1], 1ULL);
-            }
-          }
-          // computeDt of the new state (ComputeDt.h:30-34); a NaN never wins the Max
-          // reduction (Kokkos::Max joins with `>`)
-          const double cs = csound(gamma * qo[3], qo[0]);
-          const double h  = fma(cs, rdxy, fma(fabs(qo[1]), rdx, fabs(qo[2]) * rdy));
-          inv_dt_max      = (h > inv_dt_max) ? h : inv_dt_max;
-          // NaN count (SimInfo.h:624-631): h is NaN whenever a field is, so the per-field
-          // count runs only on that (rare) path
-          if (h != h)
-          {
-            const int n = (qo[0] != qo[0]) + (qo[1] != qo[1]) + (qo[2] != qo[2]) + (qo[3] != qo[3]);
-            atomicAdd(&a.kp.sc->neg[2], (unsigned long long)n);
-          }
-        }
-#pragma unroll
-        for (int f = 0; f < 4; ++f)
-          FV2D_AT(a.Qout, f) = qo[f];
-#undef FV2D_AT
-#undef FV2D_CAT
-        // multi-GPU: the slab's two edge rows are also the neighbour's ghost rows — store them
-        // straight into the neighbour's memory (peer mapping over NVLink)
-        if (peer_lo != nullptr && k < p.jbeg + 2)
-        {
-          const long long op = ocol + (long long)(p.Ny + k) * L.pitch; // its high ghost rows
-#pragma unroll
-          for (int f = 0; f < 4; ++f)
-            peer_lo[op + f * L.plane] = qo[f];
-        }
-        if (peer_hi != nullptr && k >= p.jend - 2)
-        {
-          const long long op = ocol + (long long)(k - p.Ny) * L.pitch; // its low ghost rows
-#pragma unroll
-          for (int f = 0; f < 4; ++f)
-            peer_hi[op + f * L.plane] = qo[f];
-        }
-      }
-    }
-
-    // roll the column window and the ring bookkeeping
-#if FV2D_BYTEOFF
-    offB += pitchB;
-#endif
-    if constexpr (GRAV == 2)
-    {
-      // the face below row jbeg: its hyperbolic flux will be replaced by the well-balanced one, so
-      // only the diffusive part is carried (w is uniform: 1 everywhere else, and 1 * x is exact)
-      const double w = (k + 1 == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL) ? 0.0 : 1.0;
-      fy_lo.m = w * fy_hi.m, fy_lo.t = fma(w, fy_hi.t, -dy_t), fy_lo.n = fma(w, fy_hi.n, -dy_n);
-      fy_lo.e = fma(w, fy_hi.e, -dy_e);
-    }
-    else
-      fy_lo.m = fy_hi.m, fy_lo.t = fy_hi.t - dy_t, fy_lo.n = fy_hi.n - dy_n, fy_lo.e = fy_hi.e - dy_e;
-    fy_lo.pout = fy_hi.pout;
-    Tk = Tn;
-    yp = yp1;
-    xm    = xm1;
-#pragma unroll
-    for (int f = 0; f < 4; ++f)
-      qn[f] = qnn[f];
-    sm1 = s0, s0 = s1, s1 = s2;
-    s2  = (s2 + 1 == kNS) ? 0 : s2 + 1;
+  // ring bookkeeping, carried from row to row AND from item to item: (s2, ph2) = slot / phase
+  // parity of the next Q row of the stream, (us, uph) = ... of the next U row
+  int s2 = 0, s1 = 0, s0 = 0, sm1 = 0;
+  uint32_t ph2 = 0;
+  int us = 0, us_prev = 0;
+  uint32_t uph = 0;
+  auto next_q = [&]() {
+    s2 = (s2 + 1 == kNS) ? 0 : s2 + 1;
     ph2 ^= (s2 == 0) ? 1u : 0u;
-    us_prev = us;
-    us = (us + 1 == kNU) ? 0 : us + 1;
-    uph ^= (us == 0) ? 1u : 0u;
-  }
+  };
 
-  // ---- multi-GPU: tell the neighbours how many of their ghost rows this CTA has delivered
-  if (peer_lo != nullptr || peer_hi != nullptr)
+  for (int ci = 0;; ++ci)
   {
-    const int n_lo = (peer_lo != nullptr) ? max(0, min(j1, p.jbeg + 2) - j0) : 0;
-    const int n_hi = (peer_hi != nullptr) ? max(0, j1 - max(j0, p.jend - 2)) : 0;
-    if (n_lo + n_hi > 0)
+    const WorkItem item = S.item[ci & 1];
+    if (item.j0 < 0)
+      break;
+    const int j0 = item.j0, j1 = item.j1; // rows [j0, j1) are updated
+    const int i0    = p.ibeg + item.strip * W; // first interior column of the strip
+    const int col   = i0 - 2 + t;              // this thread's column
+    const int rbase = j0 - 2;                  // first Q row of the item
+    const int rlast = j1 + 1;                  // last Q row of the item
+    const int nrow  = j1 - j0;
+    const bool interior = (t >= 2) && (t < NT - 2) && (col < p.iend);
+    const int tma_xq = tma_x0 + item.strip * W - 2;
+    const int tma_xu = tma_xq + 2;
+    // last Q row the per-row fast path may stage without looking: beyond it come the ghost rows a
+    // neighbour slab delivers (wait first) and the rows of the next item
+    const int rfast = (!PLAIN && a.kp.edge_hi == EDGE_NEIGHBOUR) ? min(rlast, p.jend - 1) : rlast;
+
+    // ghost cells of Q^{n+1} are written by the sweep that produces it: every ghost is a (sign-
+    // flipped) copy of ONE domain cell (BoundaryConditions.h:82-147, x and y passes composed), so
+    // the thread that owns the source column also stores the ghost columns mirrored from it ...
+    unsigned xmask      = 0; // bit g: ghost column g (0..Ng-1 left of the domain, Ng..2Ng-1 right) copies this column
+    const bool xstrip   = fold && (i0 < p.ibeg + Ng || (i0 + W > p.iend - Ng && i0 < p.iend));
+    if (xstrip && interior && (col < p.ibeg + Ng || col >= p.iend - Ng))
     {
-      __threadfence_system();
+      for (int g = 0; g < 2 * Ng; ++g)
+      {
+        const int ig = (g < Ng) ? g : p.iend + g - Ng;
+        if (bc_src(p.boundary_x, ig, p.ibeg, p.iend, p.Nx) == col)
+          xmask |= 1u << g;
+      }
+    }
+    // ... and the rows within Ng of the slab's edges are also stored into the ghost rows mirrored
+    // from them: this slab's own (physical boundary) or the neighbour slab's (peer mapping)
+    const bool yitem = (fold || peer_lo != nullptr || peer_hi != nullptr) && (j0 < p.jbeg + Ng || j1 > p.jend - Ng);
+
+    // ---- pre-prologue: rows j0-2, j0-1, j0 of this column (the next three rows of the Q stream)
+    double qn[4];  // q(row k+1)
+    FaceState yp;  // +y face state of row k (frame of the y normal: n = v, t = u)
+    double dyl[4]; // q(k+1) - q(k): the lower y difference of row k+1's slope, carried row to row
+    double Tk = 0.0; // temperature P / rho of (col, k) (conduction)
+    sm1 = s2;
+    mbar_wait(&S.full[s2], ph2);
+    next_q();
+    s0 = s2;
+    mbar_wait(&S.full[s2], ph2);
+    next_q();
+    s1 = s2;
+    mbar_wait(&S.full[s2], ph2);
+    next_q();
+    {
+      double qa[4], qk[4];
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+      {
+        qa[f] = S.ring[sm1][f][t];
+        qk[f] = S.ring[s0][f][t];
+        qn[f] = S.ring[s1][f][t];
+      }
+      double s[4] = {0.0, 0.0, 0.0, 0.0};
+      if constexpr (PLM)
+      {
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+          s[f] = minmod_f(qk[f] - qa[f], qn[f] - qk[f]);
+      }
+      yp.r = fma(0.5, s[0], qk[0]);
+      yp.t = fma(0.5, s[1], qk[1]);
+      yp.n = fma(0.5, s[2], qk[2]);
+      yp.p = fma(0.5, s[3], qk[3]);
+      yp.c = FACEC ? csound(gamma * yp.p, yp.r) : 0.0;
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+        dyl[f] = qn[f] - qk[f];
+      if constexpr (DIFF)
+        Tk = qk[3] * frcp(qk[0]);
+    }
+
+    FaceFlux fy_lo;  // y-face flux below row k (becomes the low face of the next row)
+    FaceState xm;    // -x face state of row k (own cell, left face), frame of the x normal
+    fy_lo.m = fy_lo.n = fy_lo.t = fy_lo.e = fy_lo.pout = 0.0;
+    xm.r = xm.n = xm.t = xm.p = xm.c = 0.0;
+
+    // Global addresses = uniform per-(array, field) base + one per-thread byte offset that is
+    // carried and bumped by a row pitch per iteration (two integer instructions per address).
+    long long offB = (L.at(0, col, 0) + (long long)(j0 - 1) * L.pitch) * (long long)sizeof(double); // row k
+
+    // the U ring: the warm-up iteration consumes no U row, so step back by one position (the roll
+    // at the end of every iteration then lands on row j0's slot)
+    uph ^= (us == 0) ? 1u : 0u;
+    us = (us == 0) ? kNU - 1 : us - 1;
+
+    if constexpr (kDead >= 0)
+    {
+      // the rows only the pre-prologue needed (rbase .. rbase+kDead) are dead once every thread has
+      // read its column: recycle their slots before the march starts
       __syncthreads();
       if (t == 0)
+      {
+#pragma unroll 1
+        for (int n = 0; n <= kDead; ++n)
+        {
+          const uint32_t slot = (uint32_t)(n == 0 ? sm1 : s0);
+          const int r = rbase + kNS + n;
+          if (r <= rlast)
+          {
+            wait_halo_row(r);
+            stage_q(tma_xq, r, slot);
+          }
+          else
+            stage_q_next(r - rlast, slot);
+        }
+      }
+    }
+
+#ifdef FV2D_TIMING
+    {
+      const long long now = clock64();
+      tm_gap += now - tm_mark, tm_mark = now, tm_items += 1 + ((long long)nrow << 16);
+    }
+#endif
+    // ---- march: iteration k finishes row k; k = j0-1 is the warm-up (no update)
+#pragma unroll kUnrollV
+    for (int k = j0 - 1; k < j1; ++k)
+    {
+      const int par = k & 1;
+      // A. new row k+2 enters; y slopes / face states of row k+1; y-face flux at k+1/2
+      mbar_wait(&S.full[s2], ph2);
+      double qnn[4];
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+        qnn[f] = S.ring[s2][f][t];
+
+      FaceState ym, yp1;
+      {
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        if constexpr (PLM)
+        {
+#pragma unroll
+          for (int f = 0; f < 4; ++f)
+          {
+            const double dup = qnn[f] - qn[f]; // also the lower difference of the next row
+            s[f]             = minmod_f(dyl[f], dup);
+            dyl[f]           = dup;
+          }
+        }
+        ym.r  = fma(-0.5, s[0], qn[0]);
+        ym.t  = fma(-0.5, s[1], qn[1]);
+        ym.n  = fma(-0.5, s[2], qn[2]);
+        ym.p  = fma(-0.5, s[3], qn[3]);
+        yp1.r = fma(0.5, s[0], qn[0]);
+        yp1.t = fma(0.5, s[1], qn[1]);
+        yp1.n = fma(0.5, s[2], qn[2]);
+        yp1.p = fma(0.5, s[3], qn[3]);
+        if constexpr (!FACEC)
+          ym.c = yp1.c = 0.0;
+        else if constexpr (PLM)
+        {
+          ym.c  = csound(gamma * ym.p, ym.r);
+          yp1.c = csound(gamma * yp1.p, yp1.r);
+        }
+        else
+        {
+          ym.c  = csound(gamma * ym.p, ym.r);
+          yp1.c = ym.c;
+        }
+      }
+      const double gdy = p.gy * p.dy, gdx = p.gx * p.dx;
+      FaceFlux fy_hi = riemann_f<SOLVER, FACEC>(yp, ym, entho, gamma, gdy, p.fslp_K);
+      // diffusive flux through the same face (between rows k and k+1), to be subtracted
+      double dy_t = 0.0, dy_n = 0.0, dy_e = 0.0, Tn = 0.0;
+      if constexpr (DIFF)
+      {
+        Tn   = qn[3] * frcp(qn[0]);
+        dy_e = kaprdy * (Tn - Tk); // FD of row k = FU of row k+1 (ThermalConduction.h:66-67)
+        {
+          const double u_lo = S.ring[s0][1][t], v_lo = S.ring[s0][2][t];
+          const ViscFlux vf = visc_face(qn[2], v_lo, qn[1], u_lo,                                        //
+                                        S.ring[s1][2][tr], S.ring[s1][2][tl], S.ring[s0][2][tr], S.ring[s0][2][tl], //
+                                        S.ring[s1][1][tr], S.ring[s1][1][tl], S.ring[s0][1][tr], S.ring[s0][1][tl], //
+                                        rdy, rdx);
+          dy_n = mudy * vf.n;
+          dy_t = mudy * vf.t;
+          dy_e = fma(mudy, vf.e, dy_e);
+        }
+      }
+
+      // B. x-face flux at the left face of (col, k): left state from the neighbour thread
+      //    (also runs, on don't-care data, in the warm-up iteration: no branch, so the x and y
+      //    Riemann problems of a row can be scheduled together)
+      {
+        FaceState xl;
+        if constexpr (PLM)
+        {
+          const double2 la = S.X1a[par][tl], lb = S.X1b[par][tl];
+          xl.r = la.x, xl.n = la.y, xl.t = lb.x, xl.p = lb.y;
+        }
+        else // PCM: the +x face state of the left neighbour is its cell state, still in the ring
+          xl.r = S.ring[s0][0][tl], xl.n = S.ring[s0][1][tl], xl.t = S.ring[s0][2][tl], xl.p = S.ring[s0][3][tl];
+        if constexpr (FACEC)
+          xl.c = S.X1c[par][tl];
+        else
+          xl.c = 0.0;
+        FaceFlux fx = riemann_f<SOLVER, FACEC>(xl, xm, entho, gamma, gdx, p.fslp_K);
+        if constexpr (DIFF)
+        {
+          // diffusive flux through the left x-face of (col, k): cells (col-1, k) and (col, k)
+          fx.e -= kaprdx * (Tk - S.X1T[par][tl]); // FL (ThermalConduction.h:64)
+          {
+            const ViscFlux vf = visc_face(S.ring[s0][1][t], S.ring[s0][1][tl], S.ring[s0][2][t], S.ring[s0][2][tl],          //
+                                          S.ring[s1][1][t], S.ring[sm1][1][t], S.ring[s1][1][tl], S.ring[sm1][1][tl], //
+                                          S.ring[s1][2][t], S.ring[sm1][2][t], S.ring[s1][2][tl], S.ring[sm1][2][tl], //
+                                          rdx, rdy);
+            fx.n = fma(-mudx, vf.n, fx.n);
+            fx.t = fma(-mudx, vf.t, fx.t);
+            fx.e = fma(-mudx, vf.e, fx.e);
+          }
+        }
+        S.X2a[par][t] = make_double2(fx.m, fx.n);
+        S.X2b[par][t] = make_double2(fx.t, fx.e);
+      }
+
+      // C. x slopes / face states of row k+1 (published for the neighbour on the right)
+      FaceState xm1;
+      {
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        if constexpr (PLM)
+        {
+#pragma unroll
+          for (int f = 0; f < 4; ++f)
+            s[f] = minmod_f(qn[f] - S.ring[s1][f][tl], S.ring[s1][f][tr] - qn[f]);
+        }
+        xm1.r = fma(-0.5, s[0], qn[0]);
+        xm1.n = fma(-0.5, s[1], qn[1]);
+        xm1.t = fma(-0.5, s[2], qn[2]);
+        xm1.p = fma(-0.5, s[3], qn[3]);
+        FaceState xp1;
+        xp1.r = fma(0.5, s[0], qn[0]);
+        xp1.n = fma(0.5, s[1], qn[1]);
+        xp1.t = fma(0.5, s[2], qn[2]);
+        xp1.p = fma(0.5, s[3], qn[3]);
+        if constexpr (!FACEC)
+          xm1.c = xp1.c = 0.0;
+        else if constexpr (PLM)
+        {
+          xm1.c = csound(gamma * xm1.p, xm1.r);
+          xp1.c = csound(gamma * xp1.p, xp1.r);
+        }
+        else
+        {
+          xm1.c = ym.c; // PCM: one sound speed per cell
+          xp1.c = ym.c;
+        }
+        if constexpr (PLM)
+        {
+          S.X1a[par ^ 1][t] = make_double2(xp1.r, xp1.n);
+          S.X1b[par ^ 1][t] = make_double2(xp1.t, xp1.p);
+        }
+        if constexpr (FACEC)
+          S.X1c[par ^ 1][t] = xp1.c;
+        if constexpr (DIFF)
+          S.X1T[par ^ 1][t] = Tn;
+      }
+
+      __syncthreads();
+
+      // E. Q rows <= k+kDead and U rows <= k-1 are dead now: refill their slots with the rows kNS /
+      // kNU further down the stream.  One block under one thread test: the other warps skip it with
+      // a single branch instead of issuing the (predicated-off) producer instructions.
+      if (t == 0)
+      {
+        const uint32_t qslot = (uint32_t)(kDead == 1 ? s1 : (kDead == 0 ? s0 : sm1));
+        if (k + kDead + kNS <= rfast)
+          stage_q(tma_xq, k + kDead + kNS, qslot);
+        else if (k + kDead + kNS > rlast)
+          stage_q_next(k + kDead + kNS - rlast, qslot);
+        else
+        {
+          wait_halo_row(k + kDead + kNS); // (a ghost row that the high neighbour delivers)
+          stage_q(tma_xq, k + kDead + kNS, qslot);
+        }
+        if (k == j1 - 8)
+        {
+          if (a.persistent)
+            pend = gridDim.x + atomicAdd(&sc->work_next, 1u);
+        }
+        else if (k == j1 - 3)
+        {
+          if (a.persistent)
+            cp_async_16(smem_u32(&S.item_in), a.items + min(pend, (unsigned)a.n_items));
+        }
+        if (k > j0)
+        {
+          if (k - 1 + kNU < j1)
+            stage_u(tma_xu, k - 1 + kNU, (uint32_t)us_prev);
+          else
+            stage_u_next(k - 1 + kNU - j1, (uint32_t)us_prev);
+        }
+      }
+
+      // D. finish row k
+      {
+        FaceFlux fxr, fxl;
+        {
+          const double2 ra = S.X2a[par][tr], rb = S.X2b[par][tr];
+          const double2 oa = S.X2a[par][t], ob = S.X2b[par][t];
+          fxr.m = ra.x, fxr.n = ra.y, fxr.t = rb.x, fxr.e = rb.y;
+          fxl.m = oa.x, fxl.n = oa.y, fxl.t = ob.x, fxl.e = ob.y;
+        }
+        // U^n of the own cell, staged by TMA two rows ago (the slot holds garbage in the warm-up
+        // iteration and for the halo threads: neither stores anything)
+        double un[4];
+        if (k >= j0)
+          mbar_wait(&S.ufull[us], uph);
+        {
+          const double *ub = &S.uring[us][0][0];
+#pragma unroll
+          for (int f = 0; f < 4; ++f)
+            un[f] = ub[f * W + tu];
+        }
+
+        // y fluxes back in the grid frame: (m, t, n, e) -> (rho, rho u, rho v, E)
+        // (fy_lo already holds hyperbolic minus diffusive flux of the face below; same for fy_hi now)
+        double fyl[4] = {fy_lo.m, fy_lo.t, fy_lo.n, fy_lo.e};
+        double fyh[4] = {fy_hi.m, fy_hi.t - dy_t, fy_hi.n - dy_n, fy_hi.e - dy_e};
+
+        double gyv = 0.0, gxv = 0.0, rho_k = 0.0;
+        if constexpr (GRAV != 0)
+        {
+          rho_k = S.ring[s0][0][t];
+          // getGravity (Gravity.h:39-57); GRAV == 2 also covers "well-balanced flux, no gravity" (g = 0)
+          if (p.gravity_mode == FV2D_GRAV_CONSTANT)
+            gxv = p.gx, gyv = p.gy;
+          else if (p.gravity_mode == FV2D_GRAV_ANALYTICAL)
+            gxv = gyv = a.kp.gtab[k];
+        }
+
+        double u4[4];
+        u4[0] = un[0] + (fxl.m - fxr.m) * dtdx + (fyl[0] - fyh[0]) * dtdy;
+        u4[1] = un[1] + (fxl.n - fxr.n) * dtdx + (fyl[1] - fyh[1]) * dtdy;
+        u4[2] = un[2] + (fxl.t - fxr.t) * dtdx + (fyl[2] - fyh[2]) * dtdy;
+        u4[3] = un[3] + (fxl.e - fxr.e) * dtdx + (fyl[3] - fyh[3]) * dtdy;
+        if constexpr (GRAV != 0)
+        {
+          // Update.h:161-166: both sweeps add into IV (Q4)
+          u4[2] += dt * rho_k * gxv + dt * rho_k * gyv;
+          u4[3] += dt * 0.5 * (fxl.m + fxr.m) * gxv + dt * 0.5 * (fyl[0] + fyh[0]) * gyv;
+        }
+
+        if constexpr (GRAV == 2)
+        {
+          // well-balanced flux at the global y boundary (Update.h:148-156): replaces the HYPERBOLIC
+          // flux of that face by {0, 0, pout -+ rho g dy, 0}; the diffusive part of the face stays.
+          // Applied as an in-place correction on the two rows it concerns (for the low face the
+          // roll below already dropped the hyperbolic part of the carried flux).
+          if (k == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL)
+            u4[2] += dtdy * (fy_hi.pout - rho_k * gyv * p.dy);
+          else if (k == p.jend - 1 && a.kp.edge_hi == EDGE_PHYSICAL)
+          {
+            u4[0] += dtdy * fy_hi.m;
+            u4[1] += dtdy * fy_hi.t;
+            u4[2] += dtdy * (fy_hi.n - (fy_lo.pout + rho_k * gyv * p.dy));
+            u4[3] += dtdy * fy_hi.e - dt * 0.5 * fy_hi.m * gyv;
+          }
+        }
+
+        if constexpr (DIFF)
+        {
+          // ThermalConduction.h:77-103: with a temperature boundary condition the reference replaces
+          // the cell's own x-flux FL (at jbeg) / FR (at jend-1) by a y-boundary expression (Q7a) -
+          // for that cell only, not for the neighbour sharing the face.  Reproduced as a correction
+          // to the face-based flux on those two rows.
+          const bool row_lo = (k == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL && p.bctc_ymin != FV2D_BCTC_NONE);
+          const bool row_hi = (k == p.jend - 1 && a.kp.edge_hi == EDGE_PHYSICAL && p.bctc_ymax != FV2D_BCTC_NONE);
+          if (tc_on && (row_lo || row_hi))
+          {
+            const double TC = S.ring[s0][3][t] * frcp(S.ring[s0][0][t]);
+            const double TL = S.ring[s0][3][tl] * frcp(S.ring[s0][0][tl]);
+            const double TR = S.ring[s0][3][tr] * frcp(S.ring[s0][0][tr]);
+            const double kap = p.kappa;
+            if (row_lo)
+            {
+              const double FL = kap * (TC - TL) * rdx;
+              const double FLb =
+                  (p.bctc_ymin == FV2D_BCTC_FIXED_TEMPERATURE) ? kap * 2.0 * (TC - p.bctc_ymin_value) * rdy : kap * p.bctc_ymin_value;
+              u4[3] += dtdx * (FL - FLb);
+            }
+            if (row_hi)
+            {
+              const double FR = kap * (TR - TC) * rdx;
+              const double FRb =
+                  (p.bctc_ymax == FV2D_BCTC_FIXED_TEMPERATURE) ? kap * 2.0 * (p.bctc_ymax_value - TC) * rdy : kap * p.bctc_ymax_value;
+              u4[3] += dtdx * (FRb - FR);
+            }
+          }
+        }
+
+        if (interior && k >= j0)
+        {
+#define FV2D_AT(base, f) (*reinterpret_cast<double *>(reinterpret_cast<char *>(base) + (f) * planeB + offB))
+#define FV2D_CAT(base, f) (*reinterpret_cast<const double *>(reinterpret_cast<const char *>(base) + (f) * planeB + offB))
+          if (U0 != nullptr) // SSP-RK2 combine (Update.h:214-220)
+          {
+#pragma unroll
+            for (int f = 0; f < 4; ++f)
+              u4[f] = 0.5 * (FV2D_CAT(U0, f) + u4[f]);
+          }
+#pragma unroll
+          for (int f = 0; f < 4; ++f)
+            FV2D_AT(a.Uout, f) = u4[f];
+
+          // consToPrim (States.h:32-43)
+          const double ir = frcp(u4[0]);
+          double qo[4];
+          qo[0] = u4[0];
+          qo[1] = u4[1] * ir;
+          qo[2] = u4[2] * ir;
+          qo[3] = fma(-0.5, fma(u4[2], qo[2], u4[1] * qo[1]), u4[3]) * gm1; // E - (rho u . u) / 2
+          // stores the x-ghost copies of this cell (row jt of array `base`, v component v2)
+          auto put_xghosts = [&](double *base, int jt, double v2) {
+#pragma unroll 1
+            for (unsigned m = xmask; m != 0; m &= m - 1)
+            {
+              const int g = __ffs(m) - 1;
+              double *d   = base + L.at(0, (g < Ng) ? g : p.iend + g - Ng, jt);
+              d[0] = qo[0], d[L.plane] = (p.boundary_x == FV2D_BC_REFLECTING) ? -qo[1] : qo[1], d[2 * L.plane] = v2,
+              d[3 * L.plane] = qo[3];
+            }
+          };
+          if (final_stage)
+          {
+            // checkNegatives (SimInfo.h:612-633): counted straight into the device counters on
+            // the (rare) event instead of carrying three counters through the sweep; one integer
+            // test of the two sign bits guards both comparisons
+            if ((__double2hiint(qo[0]) | __double2hiint(qo[3])) < 0)
+            {
+              if (qo[0] < 0.0)
+              {
+                qo[0] = a.kp.eps_reset;
+                atomicAdd(&sc->neg[0], 1ULL);
+              }
+              if (qo[3] < 0.0)
+              {
+                qo[3] = a.kp.eps_reset;
+                atomicAdd(&sc->neg[1], 1ULL);
+              }
+            }
+            // computeDt of the new state (ComputeDt.h:30-34); a NaN never wins the Max
+            // reduction (Kokkos::Max joins with `>`)
+            const double cs = csound(gamma * qo[3], qo[0]);
+            const double h  = fma(cs, rdxy, fma(fabs(qo[1]), rdx, fabs(qo[2]) * rdy));
+            inv_dt_max      = (h > inv_dt_max) ? h : inv_dt_max;
+            // NaN count (SimInfo.h:624-631): h is NaN whenever a field is, so the per-field
+            // count runs only on that (rare) path
+            if (h != h)
+            {
+              const int n = (qo[0] != qo[0]) + (qo[1] != qo[1]) + (qo[2] != qo[2]) + (qo[3] != qo[3]);
+              atomicAdd(&sc->neg[2], (unsigned long long)n);
+            }
+          }
+#pragma unroll
+          for (int f = 0; f < 4; ++f)
+            FV2D_AT(a.Qout, f) = qo[f];
+#undef FV2D_AT
+#undef FV2D_CAT
+          // ghost copies of the new row.  x: the threads next to the domain's left / right edge
+          // also store the ghost columns that mirror their column (xmask).  y: the rows within Ng of
+          // the slab's edges also go into the ghost rows that mirror them (push_ghost_rows).
+          if (xmask != 0)
+            put_xghosts(a.Qout, k, qo[2]);
+          if (yitem && (k < p.jbeg + Ng || k >= p.jend - Ng))
+          {
+            // target 0 .. 2Ng-1: this slab's own y-ghost rows at a physical boundary
+            // (BoundaryConditions.h:112-146, with the corners the x pass defines); 2Ng / 2Ng+1: the low /
+            // high neighbour slab's ghost rows, straight into its memory over NVLink
+#pragma unroll 1
+            for (int tg = 0; tg < 2 * Ng + 2; ++tg)
+            {
+              double *base = a.Qout;
+              int jt;
+              bool fv = false;
+              if (tg < 2 * Ng)
+              {
+                const int side = (tg >= Ng) ? 1 : 0;
+                jt             = side ? p.jend + tg - Ng : tg;
+                if (!fold || (side ? a.kp.edge_hi : a.kp.edge_lo) != EDGE_PHYSICAL ||
+                    bc_src(p.boundary_y, jt, p.jbeg, p.jend, p.Ny) != k)
+                  continue;
+                fv = (p.boundary_y == FV2D_BC_REFLECTING);
+              }
+              else if (tg == 2 * Ng)
+              {
+                if (peer_lo == nullptr || k >= p.jbeg + Ng)
+                  continue;
+                base = peer_lo, jt = p.Ny + k; // its high ghost rows
+              }
+              else
+              {
+                if (peer_hi == nullptr || k < p.jend - Ng)
+                  continue;
+                base = peer_hi, jt = k - p.Ny; // its low ghost rows
+              }
+              const double v2 = fv ? -qo[2] : qo[2];
+              double *d       = base + L.at(0, col, jt);
+              d[0] = qo[0], d[L.plane] = qo[1], d[2 * L.plane] = v2, d[3 * L.plane] = qo[3];
+              if (xmask != 0)
+                put_xghosts(base, jt, v2);
+            }
+          }
+        }
+      }
+
+      // roll the column window and the ring bookkeeping
+      offB += pitchB;
+      if constexpr (GRAV == 2)
+      {
+        // the face below row jbeg: its hyperbolic flux will be replaced by the well-balanced one, so
+        // only the diffusive part is carried (w is uniform: 1 everywhere else, and 1 * x is exact)
+        const double w = (k + 1 == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL) ? 0.0 : 1.0;
+        fy_lo.m = w * fy_hi.m, fy_lo.t = fma(w, fy_hi.t, -dy_t), fy_lo.n = fma(w, fy_hi.n, -dy_n);
+        fy_lo.e = fma(w, fy_hi.e, -dy_e);
+      }
+      else
+        fy_lo.m = fy_hi.m, fy_lo.t = fy_hi.t - dy_t, fy_lo.n = fy_hi.n - dy_n, fy_lo.e = fy_hi.e - dy_e;
+      fy_lo.pout = fy_hi.pout;
+      Tk = Tn;
+      yp = yp1;
+      xm    = xm1;
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+        qn[f] = qnn[f];
+      sm1 = s0, s0 = s1, s1 = s2;
+      next_q();
+      us_prev = us;
+      us = (us + 1 == kNU) ? 0 : us + 1;
+      uph ^= (us == 0) ? 1u : 0u;
+    }
+
+#ifdef FV2D_TIMING
+    {
+      const long long now = clock64();
+      tm_loop += now - tm_mark, tm_mark = now;
+    }
+#endif
+    // ---- end of the item.  Its last Q rows and its last U row are still in the rings: once every
+    // thread is done with them their slots move on down the stream.  Multi-GPU: tell the neighbours
+    // how many of their ghost rows this item has delivered.
+    int n_lo = 0, n_hi = 0;
+    if constexpr (!PLAIN)
+    {
+      n_lo = (peer_lo != nullptr) ? max(0, min(j1, p.jbeg + Ng) - j0) : 0;
+      n_hi = (peer_hi != nullptr) ? max(0, j1 - max(j0, p.jend - Ng)) : 0;
+      if (n_lo + n_hi > 0)
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (t == 0)
+    {
+      if constexpr (!PLAIN)
       {
         if (n_lo)
           atomicAdd_system(&a.kp.peer_sc[a.lo_rank]->halo_cnt[1], (unsigned long long)n_lo);
         if (n_hi)
           atomicAdd_system(&a.kp.peer_sc[a.hi_rank]->halo_cnt[0], (unsigned long long)n_hi);
       }
+      // the item's last Q rows (slots sm1 / s0 / s1 after the last roll) and its last U row move on
+      // to rows of the next item
+#pragma unroll 1
+      for (int n = 2 + kDead; n <= 3; ++n)
+        stage_q_next(n + kNS - 3, (uint32_t)(n == 1 ? sm1 : (n == 2 ? s0 : s1)));
+      stage_u_next(kNU - 1, (uint32_t)us_prev);
+      // the next item becomes the current one; the entry that landed in item_in is the one after it
+      cp_async_wait_all();
+      const WorkItem e2 = S.item_in;
+      S.item[ci & 1]    = e2;
+      publish_next(e2);
     }
   }
 
-  // ---- CTA reduction of the CFL maximum
+  // ---- CTA reduction of the CFL maximum, then the sweep's bookkeeping by its last CTA
   if (final_stage)
   {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
       inv_dt_max = fmax(inv_dt_max, __shfl_xor_sync(0xffffffffu, inv_dt_max, o));
-    __syncthreads(); // the exchange arrays are free now: reuse as scratch
-    double *red = reinterpret_cast<double *>(&S.X2a[0][0]);
-    if ((t & 31) == 0)
-      red[t >> 5] = inv_dt_max;
-    __syncthreads();
-    if (t == 0)
+  }
+  __syncthreads(); // the exchange arrays are free now: reuse as scratch
+  double *red = reinterpret_cast<double *>(&S.X2a[0][0]);
+  if ((t & 31) == 0)
+    red[t >> 5] = inv_dt_max;
+  __syncthreads();
+#ifdef FV2D_TIMING
+  if (t == 0 && blockIdx.x < 1024)
+  {
+    const long long now = clock64();
+    g_sweep_timing[blockIdx.x * 4 + 0] = tm_gap + (now - tm_mark); // everything outside the row loops
+    g_sweep_timing[blockIdx.x * 4 + 1] = tm_loop;
+    g_sweep_timing[blockIdx.x * 4 + 2] = tm_items;
+    g_sweep_timing[blockIdx.x * 4 + 3] = now - tm_start;
+  }
+#endif
+  if (t == 0)
+  {
+    if (final_stage)
     {
       double m = red[0];
       for (int w = 1; w < NT / 32; ++w)
         m = fmax(m, red[w]);
-      DevScalars *sc = a.kp.sc;
-      atomicMax(&sc->inv_acc[a.acc_slot][0], encode_ordered(m));
-      // the last CTA of the sweep mails the slab's maximum to every rank (self included):
-      // the next step's dt is reduced on the device, no host round trip
-      __threadfence();
-      const unsigned prev = atomicAdd(&sc->cta_done, 1u);
-      if (prev == gridDim.x * gridDim.y - 1)
+      atomicMax(&sc->inv_acc[1][0], encode_ordered(m));
+    }
+    __threadfence();
+    const unsigned prev = atomicAdd(&sc->cta_done, 1u);
+    if (prev == gridDim.x - 1)
+    {
+      sc->cta_done  = 0;
+      sc->work_next = 0;
+      if (final_stage)
       {
-        sc->cta_done                 = 0;
-        const unsigned long long enc = atomicMax(&sc->inv_acc[a.acc_slot][0], 0ULL);
-        post_cfl_mail(a.kp, decode_ordered(enc), a.mail_gen);
+        // the slab's maximum goes to every rank's mailbox (self included): the next step's dt is
+        // reduced on the device, no host round trip.  Then the device-side clock (main.cpp:83).
+        const unsigned long long enc = atomicExch(&sc->inv_acc[1][0], FV2D_ENC_NEG_MAX);
+        post_cfl_mail(a.kp, decode_ordered(enc), a.mail_gen + 1);
+        sc->dt                                  = dt;
+        sc->dt_hist[sc->step % FV2D_DT_HISTORY] = dt;
+        sc->t += dt;
+        sc->step += 1;
+        if (a.use_device_dt)
+          sc->inv_dt_last[0] = S.inv3[0], sc->inv_dt_last[1] = S.inv3[1], sc->inv_dt_last[2] = S.inv3[2];
       }
     }
   }
+}
+
+// Development hook (variant builds with -DFV2D_TIMING): per-CTA cycle counts of the last sweep.
+int read_sweep_timing(long long *host, int n)
+{
+#ifdef FV2D_TIMING
+  return cudaMemcpyFromSymbol(host, g_sweep_timing, sizeof(long long) * (size_t)(n < 4096 ? n : 4096)) == cudaSuccess ? 0 : 2;
+#else
+  (void)host, (void)n;
+  return 1;
+#endif
 }
 
 // --------------------------------------------------------------------------- math probe
@@ -1016,62 +1328,17 @@ void launch_math_probe(long long n, const double *a, const double *b, double *ou
   k_math_probe<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, a, b, out_rcp, out_cs);
 }
 
-// --------------------------------------------------------------------------- step prologue
+// --------------------------------------------------------------------------- stand-alone ghost fill
 
-__device__ __forceinline__ int bc_src(int bc, int k, int beg, int end, int N)
-{
-  switch (bc)
-  {
-  case FV2D_BC_REFLECTING:
-    return 2 * (k < beg ? beg : end) - k - 1;
-  case FV2D_BC_PERIODIC:
-    return k < beg ? k + N : k - N;
-  default:
-    return k < beg ? beg : end - 1;
-  }
-}
-
-// Ghost fill (BoundaryConditions.h:82-147; x and y passes composed, see fv2d_ops.cu) plus
-// the device-side clock: dt = CFL / max(inverse time-steps) (ComputeDt.h:64), t += dt
-// (main.cpp:83).
-__global__ void k_step_begin(KParams kp, double *__restrict__ Q, StepBeginArgs a)
+// Ghost fill of a Q array whose ghosts were not written by a sweep (after an upload, after the
+// operator-level calls, and to complete the array that fv2d_advance_host hands back): the x and
+// y passes of BoundaryConditions.h:82-147 composed (see fv2d_ops.cu).  Ghost rows on a
+// neighbour-slab side are left to the halo exchange: the kernel waits until the neighbour has
+// pushed all of them, then applies the x boundary condition to their x-ghost columns.
+__global__ void k_fill_ghosts(KParams kp, double *__restrict__ Q, unsigned long long halo_expected)
 {
   const fv2d_device_params &p = kp.p;
   const long long tid         = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid == 0)
-  {
-    DevScalars *sc = kp.sc;
-    if (a.advance)
-    {
-      double dt;
-      if (a.use_device_dt)
-      {
-        const double hyp = collect_cfl_mail(kp, a.mail_gen);
-        double tc = p.epsilon, visc = p.epsilon;
-        if (p.thermal_conductivity_active)
-          tc = fmax(2.0 * p.kappa / (p.dx * p.dx), 2.0 * p.kappa / (p.dy * p.dy));
-        if (p.viscosity_active)
-          visc = fmax(2.0 * p.mu / (p.dx * p.dx), 2.0 * p.mu / (p.dy * p.dy));
-        double m = hyp;
-        if (m < tc)
-          m = tc;
-        if (m < visc)
-          m = visc;
-        sc->inv_dt_last[0] = hyp;
-        sc->inv_dt_last[1] = tc;
-        sc->inv_dt_last[2] = visc;
-        dt                 = p.CFL / m;
-      }
-      else
-        dt = a.dt_host;
-      sc->dt                                    = dt;
-      sc->dt_hist[sc->step % FV2D_DT_HISTORY]   = dt;
-      sc->t += dt;
-      sc->step += 1;
-      sc->inv_acc[a.acc_reset][0] = FV2D_ENC_NEG_MAX;
-    }
-  }
-
   const int Ng = p.Ng, Ntx = p.Ntx;
   const long long n_y = 2LL * Ng * Ntx, n_x = 2LL * Ng * p.Ny;
   if (tid >= n_y + n_x)
@@ -1098,11 +1365,9 @@ __global__ void k_step_begin(KParams kp, double *__restrict__ Q, StepBeginArgs a
     const int side = (j < p.jbeg) ? 0 : 1;
     if ((side == 0 ? kp.edge_lo : kp.edge_hi) != EDGE_PHYSICAL)
     {
-      // ghost rows owned by the halo exchange: the neighbour pushed the domain columns; once
-      // they have all arrived, apply the x boundary condition to the row's own x-ghosts
       if (i >= p.ibeg && i < p.iend)
         return;
-      wait_ge_sys(&kp.sc->halo_cnt[side], a.halo_expected, kp.sc);
+      wait_ge_sys(&kp.sc->halo_cnt[side], halo_expected, kp.sc);
     }
     else
     {
@@ -1123,10 +1388,10 @@ __global__ void k_step_begin(KParams kp, double *__restrict__ Q, StepBeginArgs a
   Q[od + 3 * kp.L.plane]  = pr;
 }
 
-void launch_step_begin(const KParams &kp, double *Q, const StepBeginArgs &a, cudaStream_t s)
+void launch_fill_ghosts(const KParams &kp, double *Q, unsigned long long halo_expected, cudaStream_t s)
 {
   const long long n = 2LL * kp.p.Ng * kp.p.Ntx + 2LL * kp.p.Ng * kp.p.Ny;
-  k_step_begin<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(kp, Q, a);
+  k_fill_ghosts<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(kp, Q, halo_expected);
 }
 
 // --------------------------------------------------------------------------- dispatch
@@ -1149,10 +1414,8 @@ static cudaError_t launch_variant(const CUtensorMap &tmQ, const CUtensorMap &tmU
   static_assert(kNT != 256 || smem <= 115712, "two CTAs per SM need <= 113 KB of shared memory each");
   if (configure_only)
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const int W       = kNT - 4;
-  const int nstrips = (a.kp.p.Nx + W - 1) / W;
-  const int nchunks = (a.kp.p.Ny + a.chunk_rows - 1) / a.chunk_rows;
-  kern<<<dim3(nstrips, nchunks), kNT, smem, s>>>(tmQ, tmU, a);
+  // persistent: CTA b starts on work item b and pulls the others from the device-wide counter
+  kern<<<a.n_ctas, kNT, smem, s>>>(tmQ, tmU, a);
   return cudaGetLastError();
 }
 

@@ -176,6 +176,12 @@ int fv2d_get_negative_counts(fv2d_ctx *ctx, uint64_t counts[3], int reset);
  * diagnostic, python/plot_energy_evolution.py:28-47). */
 int fv2d_integrate_mass_energy(fv2d_ctx *ctx, double *mass, double *energy);
 
+/* 64-bit hash of the raw bits of the conserved state U of the local slab, keyed by GLOBAL cell
+ * index and summed modulo 2^64: independent of cell order and of the slab decomposition, so the
+ * wrapping sum of the slab hashes of an N-GPU run equals the hash of the same state on one GPU
+ * (the multi-GPU contract is bitwise equality; main.cpp:62-84 has no counterpart). */
+int fv2d_state_hash(fv2d_ctx *ctx, uint64_t *hash);
+
 /* Measurement hooks (bench.py): when enabled, every sweep launch is bracketed by a pair of
  * CUDA events on the context's stream; fv2d_profile_read synchronises and returns the summed
  * sweep time, the number of sweep launches and the number of all kernel launches since
@@ -188,6 +194,23 @@ int fv2d_profile_read(fv2d_ctx *ctx, double *sweep_ms, int64_t *sweep_launches, 
  * `device`: out_rcp[i] = 1 / a[i], out_cs[i] = sqrt(a[i] / b[i]) as the sweep computes them
  * (States.h:46 speedOfSound with a = gamma0 * P, b = rho). */
 int fv2d_debug_math_probe(int device, int64_t n, const double *a, const double *b, double *out_rcp, double *out_cs);
+
+/* Measurement hook: the fp64 pipe's peak on CUDA device `device`, in thread-level DFMA
+ * instructions per second (independent dependent-DFMA chains, best of 3 timed launches): the
+ * denominator of the second roofline (FP64-pipe utilisation) bench.py reports. */
+int fv2d_debug_fp64_peak(int device, double *dfma_per_second);
+
+/* Test hook (host only, needs no GPU): the row runs [first, last) - relative to the first domain row
+ * of the slab - into which the persistent sweep cuts a slab of Nx x Ny_local cells on a device with
+ * num_sms SMs, in table order (every run is crossed with every strip of 252 columns to give the work
+ * items).  runs receives up to max_runs (first, last) pairs, *n_runs the number of runs. */
+int fv2d_debug_schedule(int Nx, int Ny_local, int num_sms, int neighbour_lo, int neighbour_hi, int32_t *runs, int max_runs,
+                        int *n_runs);
+
+/* Development hook (only in library variants built with -DFV2D_TIMING; FV2D_ERR_ARG otherwise):
+ * per CTA of the last sweep, 4 values: clock cycles outside the row loops, inside them, work items
+ * processed, total. */
+int fv2d_debug_sweep_timing(fv2d_ctx *ctx, int64_t *out, int n);
 
 /* Host-buffer convenience used for end-to-end measurement: upload Q (pinned or pageable
  * host memory), primToCons, computeDt, run `nsteps` fused steps, download Q; dts (may be

@@ -7,7 +7,7 @@ WL=kelvin_helmholtz_8192_plm_hllc
 if [ "$1" == "--workload" ]; then WL=$2; shift 2; fi
 for n in "$@"; do
   lib=scratch/lib_$n.so; [ "$n" == "main" ] && lib=fv2d_b200/libfv2d_b200.so
-  FV2D_B200_LIB=$PWD/$lib timeout 150 python bench.py --workload $WL --steps 40 --warmup 5 --e2e-steps 0 --no-cpu-baseline $BENCH_EXTRA 2>&1 | tail -1 > gpurun_out/var_${WL}_$n.json
+  FV2D_B200_LIB=$PWD/$lib timeout 150 python bench.py --workload $WL --steps 40 --warmup 5 --e2e-steps 0 --no-cpu-baseline --reps 1 --sustained-steps 0 --no-scaling-blocks $BENCH_EXTRA 2>&1 | tail -1 > gpurun_out/var_${WL}_$n.json
   python - "$n" gpurun_out/var_${WL}_$n.json <<'PY'
 import json,sys
 try:

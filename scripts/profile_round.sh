@@ -10,13 +10,13 @@ mkdir -p gpurun_out
 python bench.py 2> gpurun_out/${tag}_bench.err | tail -1 > gpurun_out/${tag}_bench.json
 python bench.py --impl reference --steps 10 --warmup 3 2>> gpurun_out/${tag}_bench.err | tail -1 > gpurun_out/${tag}_bench_reference_arm.json
 for wl in blast_4096_pcm_hllc rayleigh_taylor_16384_plm_hllc c91_8192_pcm_hllc_tc_visc; do
-  python bench.py --workload $wl --steps 40 --warmup 5 --e2e-steps 0 --no-cpu-baseline 2>> gpurun_out/${tag}_bench.err | tail -1 > gpurun_out/${tag}_bench_$wl.json
+  python bench.py --workload $wl --steps 40 --warmup 5 --e2e-steps 0 --no-cpu-baseline --reps 1 --sustained-steps 0 --no-scaling-blocks 2>> gpurun_out/${tag}_bench.err | tail -1 > gpurun_out/${tag}_bench_$wl.json
 done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_kh8192.csv \
-  python bench.py --steps 4 --warmup 3 --e2e-steps 0 --no-cpu-baseline > gpurun_out/${tag}_launches.log 2>&1
+  python bench.py --steps 4 --warmup 3 --e2e-steps 0 --no-cpu-baseline --reps 1 --sustained-steps 0 --no-scaling-blocks > gpurun_out/${tag}_launches.log 2>&1
 for wl in kelvin_helmholtz_8192_plm_hllc c91_8192_pcm_hllc_tc_visc; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sweep -s 4 -c 1 -f -o gpurun_out/${tag}_sweep_$wl \
-    python bench.py --workload $wl --steps 3 --warmup 3 --e2e-steps 0 --no-cpu-baseline > gpurun_out/${tag}_ncu_$wl.log 2>&1
+    python bench.py --workload $wl --steps 3 --warmup 3 --e2e-steps 0 --no-cpu-baseline --reps 1 --sustained-steps 0 --no-scaling-blocks > gpurun_out/${tag}_ncu_$wl.log 2>&1
 done
 for f in gpurun_out/${tag}_bench*.json; do python - $f <<'PY'
 import json,sys

@@ -6,7 +6,7 @@ timeout 400 python -m pytest tests/test_gpu_multigpu.py -x -q 2>&1 | tail -3
 run() { # workload N steps
   local wl=$1 n=$2 steps=$3 port=$((29500 + RANDOM % 400))
   if [ "$n" == "1" ]; then
-    timeout 300 python bench.py --workload $wl --steps $steps --warmup 5 --e2e-steps 0 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/scale_${wl}_n$n.json
+    timeout 300 python bench.py --workload $wl --steps $steps --warmup 5 --e2e-steps 0 --no-cpu-baseline --reps 1 --sustained-steps 0 --no-scaling-blocks 2>&1 | tail -1 > gpurun_out/scale_${wl}_n$n.json
   else
     timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port \
       bench.py --gpus $n --workload $wl --steps $steps --warmup 5 2>&1 | tail -1 > gpurun_out/scale_${wl}_n$n.json
