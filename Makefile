@@ -18,15 +18,22 @@ $(OBJDIR)/fv2d_ops.o: $(CSRC)/fv2d_ops.cu $(HOSTHDR)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) --fmad=false -c $< -o $@
 
+# the fused sweep: dispatcher + small kernels, and one translation unit per Riemann solver
+# (0 = HLL, 1 = HLLC, 2 = FSLP) holding that solver's 36 kernel instantiations (parallel under -j)
 $(OBJDIR)/fv2d_sweep.o: $(CSRC)/fv2d_sweep.cu $(HOSTHDR)
 	@mkdir -p $(OBJDIR)
-	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(OBJDIR)/fv2d_sweep.ptxas.log || (cat $(OBJDIR)/fv2d_sweep.ptxas.log; false)
+	$(NVCC) $(NVFLAGS) $(SWEEPFLAGS) -c $< -o $@
+
+$(OBJDIR)/fv2d_sweep_s%.o: $(CSRC)/fv2d_sweep.cu $(HOSTHDR)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) $(SWEEPFLAGS) -DFV2D_SOLVER_ONLY=$* -Xptxas -v -c $< -o $@ 2> $(OBJDIR)/fv2d_sweep_s$*.ptxas.log || (cat $(OBJDIR)/fv2d_sweep_s$*.ptxas.log; false)
 
 $(OBJDIR)/fv2d_capi.o: $(CSRC)/fv2d_capi.cu $(HOSTHDR)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -Xcompiler -fopenmp -c $< -o $@
 
-$(LIB): $(OBJDIR)/fv2d_ops.o $(OBJDIR)/fv2d_sweep.o $(OBJDIR)/fv2d_capi.o
+SWEEPOBJ := $(OBJDIR)/fv2d_sweep.o $(OBJDIR)/fv2d_sweep_s0.o $(OBJDIR)/fv2d_sweep_s1.o $(OBJDIR)/fv2d_sweep_s2.o
+$(LIB): $(OBJDIR)/fv2d_ops.o $(SWEEPOBJ) $(OBJDIR)/fv2d_capi.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static -Xcompiler -fopenmp
 
 fv2d_b200/fv2d_b200_main: fv2d_b200/host/main.cpp $(HOSTHDR) $(LIB)

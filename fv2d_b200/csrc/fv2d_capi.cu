@@ -9,6 +9,8 @@
 
 #include <unistd.h>
 
+#include <nvtx3/nvToolsExt.h> // header-only NVTX3: no link dependency, no cost unless a tool is attached
+
 #include "../host/Init.h"
 #include "../host/SimInfo.h"
 #include "../host/SnapshotIO.h"
@@ -16,6 +18,15 @@
 
 namespace fv2d
 {
+
+// NVTX range named like the reference's Kokkos kernel label (what Kokkos-tools / Nsight show for the
+// reference: Update.h:67,102,215, ComputeDt.h:27, BoundaryConditions.h:89,119, ThermalConduction.h:43,
+// Viscosity.h:34, SimInfo.h:580,593,611), so a timeline of this library reads like one of the reference.
+struct NvtxRange
+{
+  explicit NvtxRange(const char *label) { nvtxRangePushA(label); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 static thread_local std::string g_last_error;
 void set_error(const std::string &msg) { g_last_error = msg; }
@@ -227,19 +238,32 @@ static int ensure_ustar(fv2d_ctx *c)
 static int euler_step_ops(fv2d_ctx *c, double *Q, double *Unew, double dt)
 {
   int rc;
-  launch_fill_boundaries(c->kp, Q, c->stream);
+  {
+    NvtxRange r("Filling X-boundary + Filling Y-boundary");
+    launch_fill_boundaries(c->kp, Q, c->stream);
+  }
   if (c->kp.p.reconstruction == FV2D_PLM)
   {
     if ((rc = ensure_slopes(c)))
       return rc;
+    NvtxRange r("Slopes");
     launch_compute_slopes(c->kp, Q, c->slopesX, c->slopesY, c->stream);
   }
   // (PCM never reads the slope arrays: Update.h:27-33)
-  launch_fluxes_and_update(c->kp, Q, c->slopesX, c->slopesY, Unew, dt, c->stream);
+  {
+    NvtxRange r("Update");
+    launch_fluxes_and_update(c->kp, Q, c->slopesX, c->slopesY, Unew, dt, c->stream);
+  }
   if (c->kp.p.thermal_conductivity_active)
+  {
+    NvtxRange r("Thermal conduction");
     launch_thermal_conduction(c->kp, Q, Unew, dt, c->stream);
+  }
   if (c->kp.p.viscosity_active)
+  {
+    NvtxRange r("Viscosity");
     launch_viscosity(c->kp, Q, Unew, dt, c->stream);
+  }
   FV2D_CUDA(cudaGetLastError());
   return FV2D_OK;
 }
@@ -345,11 +369,15 @@ static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
   const int cur = c->cur, nxt = cur ^ 1;
   const unsigned long long pps = pushes_per_sweep(c);
   auto fill_ghosts = [&](double *Q) {
+    NvtxRange r("Filling X-boundary + Filling Y-boundary");
     launch_fill_ghosts(c->kp, Q, c->halo_gen * pps, c->stream);
     c->n_launch_total++;
   };
   if (!c->ghosts_valid || !c->fold_ok)
     fill_ghosts(c->Q[cur]);
+  // one range per step; the fused sweep stands for the reference's whole kernel chain
+  NvtxRange step_range("Slopes + Update + Thermal conduction + Viscosity + Conservative to Primitive + Check negative "
+                       "density/pressure + Computing DT (fused sweep)");
   auto prof_mark = [&](int which) {
     if (c->profile && c->prof_n < kProfMax)
       cudaEventRecord(c->prof_ev[2 * c->prof_n + which], c->stream);
@@ -379,6 +407,7 @@ static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
     a.peer_lo_Qout  = (c->kp.edge_lo == EDGE_NEIGHBOUR) ? c->peerQ_lo[qout] : nullptr;
     a.peer_hi_Qout  = (c->kp.edge_hi == EDGE_NEIGHBOUR) ? c->peerQ_hi[qout] : nullptr;
     a.halo_expected = c->halo_gen * pps;
+    a.peer_lo_Ny = c->peer_lo_Ny, a.peer_lo_plane = c->peer_lo_plane, a.peer_hi_plane = c->peer_hi_plane;
   };
   cudaError_t e;
   if (c->time_stepping == FV2D_TS_RK2)
@@ -433,6 +462,7 @@ static int compute_dt_now(fv2d_ctx *c)
     return arg_fail("multi-GPU context: call fv2d_halo_connect before computing dt");
   static const unsigned long long init = FV2D_ENC_NEG_MAX;
   FV2D_CUDA(cudaMemcpyAsync(&c->sc->inv_acc[0][0], &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+  NvtxRange r("Computing DT");
   launch_compute_dt(c->kp, c->Q[c->cur], &c->sc->inv_acc[0][0], c->stream);
   c->mail_gen++;
   launch_finalize_dt(c->kp, &c->sc->inv_acc[0][0], c->mail_gen, c->stream);
@@ -618,10 +648,14 @@ int fv2d_ctx_create_slab(const fv2d_device_params *dev, int time_stepping, doubl
   int rc;
   if ((rc = check_supported(*dev)))
     return rc;
-  if (nranks < 1 || rank < 0 || rank >= nranks || dev->Ny % nranks != 0)
-    return arg_fail("bad slab decomposition: Ny must be divisible by nranks");
+  if (nranks < 1 || rank < 0 || rank >= nranks || dev->Ny < nranks)
+    return arg_fail("bad slab decomposition: need 0 <= rank < nranks <= Ny");
   if (time_stepping != FV2D_TS_EULER && time_stepping != FV2D_TS_RK2)
     return arg_fail("time_stepping must be FV2D_TS_EULER or FV2D_TS_RK2");
+  if (nranks > kMaxRanks)
+    return arg_fail("at most 8 y-slabs (one NVSwitch box) are supported");
+  if (nranks > 1 && dev->Ny / nranks < 2 * dev->Ng)
+    return arg_fail("slab thinner than the ghost layer");
 
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -651,12 +685,13 @@ int fv2d_ctx_create_slab(const fv2d_device_params *dev, int time_stepping, doubl
 
   KParams &kp  = c->kp;
   kp.p         = *dev;
-  const int Nyl = dev->Ny / nranks;
+  // rows are dealt out as evenly as they go: the first Ny % nranks slabs get one row more
+  const int Nyl = dev->Ny / nranks + (rank < dev->Ny % nranks ? 1 : 0);
   kp.p.Ny       = Nyl;
   kp.p.Nty      = Nyl + 2 * dev->Ng;
   kp.p.jend     = dev->Ng + Nyl;
   kp.Ny_global  = dev->Ny;
-  kp.j_global_offset = rank * Nyl;
+  kp.j_global_offset = rank * (dev->Ny / nranks) + std::min(rank, dev->Ny % nranks);
   const bool periodic_y = dev->boundary_y == FV2D_BC_PERIODIC;
   kp.edge_lo = (rank == 0 && !(periodic_y && nranks > 1)) ? EDGE_PHYSICAL : EDGE_NEIGHBOUR;
   kp.edge_hi = (rank == nranks - 1 && !(periodic_y && nranks > 1)) ? EDGE_PHYSICAL : EDGE_NEIGHBOUR;
@@ -664,16 +699,6 @@ int fv2d_ctx_create_slab(const fv2d_device_params *dev, int time_stepping, doubl
   kp.rank      = rank;
   kp.nranks    = nranks;
   c->num_sms   = prop.multiProcessorCount;
-  if (nranks > kMaxRanks)
-  {
-    delete c;
-    return arg_fail("at most 8 y-slabs (one NVSwitch box) are supported");
-  }
-  if (nranks > 1 && Nyl < 2 * dev->Ng)
-  {
-    delete c;
-    return arg_fail("slab thinner than the ghost layer");
-  }
 
   Layout &L = kp.L;
   L.lead    = (16 - dev->ibeg % 16) % 16;
@@ -872,6 +897,7 @@ int fv2d_download_U(fv2d_ctx *c, double *hostU)
 int fv2d_prim_to_cons(fv2d_ctx *c)
 {
   FV2D_ENTER(c);
+  NvtxRange r("Primitive to Conservative");
   launch_prim_to_cons(c->kp, c->Q[c->cur], c->U, c->stream);
   FV2D_CUDA(cudaGetLastError());
   return FV2D_OK;
@@ -880,6 +906,7 @@ int fv2d_cons_to_prim(fv2d_ctx *c)
 {
   FV2D_ENTER(c);
   c->ghosts_valid = c->dt_valid = false; // Q is rewritten over range_tot
+  NvtxRange r("Conservative to Primitive");
   launch_cons_to_prim(c->kp, c->U, c->Q[c->cur], c->stream);
   FV2D_CUDA(cudaGetLastError());
   return FV2D_OK;
@@ -892,7 +919,10 @@ int fv2d_check_negatives(fv2d_ctx *c, uint64_t counts[3])
   if ((rc = read_scalars(c)))
     return rc;
   unsigned long long before[3] = {c->sc_host->neg[0], c->sc_host->neg[1], c->sc_host->neg[2]};
-  launch_check_negatives(c->kp, c->Q[c->cur], c->sc->neg, c->stream);
+  {
+    NvtxRange r("Check negative density/pressure");
+    launch_check_negatives(c->kp, c->Q[c->cur], c->sc->neg, c->stream);
+  }
   FV2D_CUDA(cudaGetLastError());
   if ((rc = read_scalars(c)))
     return rc;
@@ -983,7 +1013,10 @@ int fv2d_update(fv2d_ctx *c, double dt)
   launch_cons_to_prim(c->kp, c->Ustar, Q, c->stream);
   if ((rc = euler_step_ops(c, Q, c->U, dt)))
     return rc;
-  launch_rk2_correct(c->kp, U0, c->U, c->stream);
+  {
+    NvtxRange r("RK2 Correct");
+    launch_rk2_correct(c->kp, U0, c->U, c->stream);
+  }
   FV2D_CUDA(cudaGetLastError());
   return FV2D_OK;
 }
@@ -1175,7 +1208,7 @@ int fv2d_debug_sweep_timing(fv2d_ctx *c, int64_t *out, int n)
   int rc = sync_ctx(c);
   if (rc)
     return rc;
-  rc = read_sweep_timing((long long *)out, n);
+  rc = read_sweep_timing(c->kp.p.riemann_solver, (long long *)out, n);
   if (rc == 1)
     return arg_fail("this build of the library has no sweep timing (rebuild with -DFV2D_TIMING)");
   if (rc)
@@ -1332,6 +1365,8 @@ struct HaloHandle
   cudaIpcMemHandle_t mem[3]; // Q[0], Q[1], scalars
   uint64_t offset[3];        // of the pointer inside its cudaMalloc allocation
   uint64_t raw[3];           // same-process shortcut: the device pointers themselves
+  int64_t plane;             // doubles per field plane of this rank's arrays (slabs may differ by a row)
+  int32_t ny_local;          // rows this rank owns
 };
 static_assert(sizeof(HaloHandle) <= FV2D_IPC_HANDLE_BYTES, "handle too large");
 
@@ -1356,7 +1391,9 @@ int fv2d_halo_export(fv2d_ctx *c, void *handle)
   h.rank   = c->rank;
   h.nranks = c->nranks;
   h.device = c->device;
-  h.pid    = (int64_t)getpid();
+  h.pid      = (int64_t)getpid();
+  h.plane    = c->kp.L.plane;
+  h.ny_local = c->kp.p.Ny;
   void *ptrs[3] = {c->Q[0], c->Q[1], c->sc};
   for (int k = 0; k < 3; ++k)
   {
@@ -1423,13 +1460,16 @@ int fv2d_halo_connect(fv2d_ctx *c, const void *handles, int nranks)
     c->kp.peer_sc[q] = (DevScalars *)ptr[2];
     if (q == lo && need_lo)
     {
-      c->peerQ_lo[0] = (double *)ptr[0];
-      c->peerQ_lo[1] = (double *)ptr[1];
+      c->peerQ_lo[0]  = (double *)ptr[0];
+      c->peerQ_lo[1]  = (double *)ptr[1];
+      c->peer_lo_Ny    = h.ny_local;
+      c->peer_lo_plane = h.plane;
     }
     if (q == hi && need_hi)
     {
-      c->peerQ_hi[0] = (double *)ptr[0];
-      c->peerQ_hi[1] = (double *)ptr[1];
+      c->peerQ_hi[0]  = (double *)ptr[0];
+      c->peerQ_hi[1]  = (double *)ptr[1];
+      c->peer_hi_plane = h.plane;
     }
   }
   c->connected = true;

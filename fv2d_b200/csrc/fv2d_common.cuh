@@ -237,6 +237,8 @@ struct fv2d_ctx
 
   // multi-GPU peers (slab below / above): the neighbours' Q[0], Q[1] mapped into this device
   double *peerQ_lo[2], *peerQ_hi[2];
+  int peer_lo_Ny;                          // rows the low neighbour owns (its high ghost rows start at Ng + that)
+  long long peer_lo_plane, peer_hi_plane;  // plane strides of the neighbours' arrays (slabs may differ by a row)
   void *ipc_opened[24];
   int n_ipc_opened;
   bool connected;

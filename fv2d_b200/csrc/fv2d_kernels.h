@@ -53,6 +53,8 @@ struct SweepArgs
   // stage epilogue stores its edge rows straight into the neighbour's ghost rows.
   double *peer_lo_Qout, *peer_hi_Qout;
   int lo_rank, hi_rank;
+  int peer_lo_Ny;                         // rows the low neighbour owns
+  long long peer_lo_plane, peer_hi_plane; // plane strides of the neighbours' arrays
   unsigned long long mail_gen;      // generation of the CFL mails this step's dt is made of; the final stage posts mail_gen + 1
   unsigned long long halo_expected; // ghost rows each neighbour must have pushed before they are read
 };
@@ -62,7 +64,7 @@ cudaError_t launch_sweep(const CUtensorMap &tmapQ, const CUtensorMap &tmapU, con
 // Opt-in dynamic shared memory etc.; call once per process before the first sweep.
 cudaError_t sweep_configure();
 int sweep_strip_width();
-int read_sweep_timing(long long *host, int n); // development hook: 0 ok, 1 not compiled in, 2 CUDA error
+int read_sweep_timing(int solver, long long *host, int n); // development hook: 0 ok, 1 not compiled in, 2 CUDA error
 // Accuracy probe of the sweep's reciprocal / sound-speed primitives (device pointers).
 void launch_math_probe(long long n, const double *a, const double *b, double *out_rcp, double *out_cs, cudaStream_t s);
 

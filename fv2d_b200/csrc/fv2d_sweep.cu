@@ -458,9 +458,11 @@ struct SweepSmem
 };
 
 // GRAV: 0 = no gravity, 1 = gravity, 2 = gravity + well-balanced flux at the y boundary
-// PLAIN: the common launch - the only stage of a forward-Euler step on a slab without neighbours -
-// whose loop-invariant tests (RK2 combine, peer pushes, final_stage) are resolved at compile time
-// instead of once per row.
+// MODE: what kind of stage the launch is, so that its loop-invariant tests are resolved at compile
+// time instead of once per row (and their code stays out of the row loop):
+//   kPlain   the only stage of a forward-Euler step on a slab without neighbours (the common launch)
+//   kMulti   the same on a y-slab with neighbour slabs (peer pushes, halo waits)
+//   kGeneral anything: either stage of an SSP-RK2 step, with or without neighbours
 //
 // Persistent: the grid is min(#work items, 2 x #SMs) CTAs.  A work item is (strip, rows j0..j1-1);
 // CTA b starts on item b and then pulls further items from a device-wide counter.  The two TMA
@@ -473,7 +475,13 @@ struct SweepSmem
 // they unbalance the tail); every item has at least 8 rows, so a stream never runs past the next
 // item.  The row loop contains no function call and no table walk: calls inside it made ptxas keep
 // the ring bookkeeping in vector registers instead of uniform ones (+70 IMAD per row, spills).
-template <int NT, bool PLM, int SOLVER, int GRAV, bool DIFF, bool PLAIN>
+enum : int
+{
+  kPlain = 0,
+  kMulti = 1,
+  kGeneral = 2
+};
+template <int NT, bool PLM, int SOLVER, int GRAV, bool DIFF, int MODE>
 __global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : (NT <= 256 ? 2 : 1)))
 k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmU,
         const __grid_constant__ SweepArgs a)
@@ -496,8 +504,9 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
   const fv2d_device_params &p = a.kp.p;
   const Layout &L             = a.kp.L;
   DevScalars *const sc        = a.kp.sc;
-  const double *const U0      = PLAIN ? nullptr : a.U0;
-  const bool final_stage      = PLAIN ? true : (a.final_stage != 0);
+  constexpr bool PLAIN        = (MODE == kPlain);
+  const double *const U0      = (MODE == kGeneral) ? a.U0 : nullptr;
+  const bool final_stage      = (MODE == kGeneral) ? (a.final_stage != 0) : true;
   double *const peer_lo       = PLAIN ? nullptr : a.peer_lo_Qout;
   double *const peer_hi       = PLAIN ? nullptr : a.peer_hi_Qout;
   const int Ng                = p.Ng;
@@ -530,27 +539,32 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
   // tail.  Nobody waits for the atomic or for the table read that follows it 5 rows later (cp.async
   // into shared memory): both have landed when the item ends.
   unsigned pend = 0; // requested table index (thread 0)
-  // ghost rows owned by a neighbour slab: its sweep of the previous stage pushed them (plain stores
-  // over NVLink); wait for all of them, then order those writes before the async-proxy reads of TMA
-  auto wait_halo_row = [&](int r) {
+  // Ghost rows owned by a neighbour slab: its sweep of the previous stage pushed them (plain stores
+  // over NVLink).  Before the first row of an item that reads such rows is staged, wait for all of
+  // them, then order those writes before the async-proxy reads of TMA.  (After a final-stage sweep
+  // the wait never spins: the CFL mail this sweep has already received is posted after the
+  // neighbour's last push.  It does between the two stages of an RK2 step.)  Called when an item is
+  // published as the next one, outside the row loop.
+  auto wait_halo_item = [&](const WorkItem &e) {
     if constexpr (!PLAIN)
     {
-      const int side = (r < p.jbeg) ? 0 : 1;
-      if ((r < p.jbeg || r >= p.jend) && (side == 0 ? a.kp.edge_lo : a.kp.edge_hi) == EDGE_NEIGHBOUR)
-      {
-        wait_ge_sys(&sc->halo_cnt[side], a.halo_expected, sc);
+      if (e.j0 < 0)
+        return;
+      const bool lo = e.j0 - 2 < p.jbeg && a.kp.edge_lo == EDGE_NEIGHBOUR;
+      const bool hi = e.j1 + 1 >= p.jend && a.kp.edge_hi == EDGE_NEIGHBOUR;
+      if (lo)
+        wait_ge_sys(&sc->halo_cnt[0], a.halo_expected, sc);
+      if (hi)
+        wait_ge_sys(&sc->halo_cnt[1], a.halo_expected, sc);
+      if (lo || hi)
         fence_proxy_async();
-      }
     }
   };
   // Q row `off` (>= 1) rows beyond the last Q row of the current item = row off-1 of the next item
   auto stage_q_next = [&](int off, uint32_t slot) {
     const int r = S.nx_rbase + off - 1;
     if (r <= S.nx_rlast)
-    {
-      wait_halo_row(r);
       stage_q(S.nx_xq, r, slot);
-    }
   };
   // U row `off` (>= 0) rows beyond the last U row of the current item
   auto stage_u_next = [&](int off, uint32_t slot) {
@@ -559,6 +573,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
       stage_u(S.nx_xq + 2, r, slot);
   };
   auto publish_next = [&](const WorkItem &e) { // thread 0: e is the item after the current one
+    wait_halo_item(e);
     S.nx_xq    = tma_x0 + e.strip * W - 2;
     S.nx_rbase = e.j0 - 2;
     S.nx_rlast = (e.j0 < 0) ? e.j0 - 3 : e.j1 + 1;
@@ -587,16 +602,14 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
     S.item_in = WorkItem{0, -1, -1, 0};
     const WorkItem e1 = a.items[i1]; // items[n_items] is the end marker
     S.item[0] = e0, S.item[1] = e1;
+    wait_halo_item(e0);
     publish_next(e1);
     // initial fill of both rings from the first item (>= 8 rows unless it is the CTA's only one)
     {
       const int x = tma_x0 + e0.strip * W - 2;
 #pragma unroll 1
       for (int n = 0; n < kNS && n < e0.j1 - e0.j0 + 4; ++n)
-      {
-        wait_halo_row(e0.j0 - 2 + n);
         stage_q(x, e0.j0 - 2 + n, (uint32_t)n);
-      }
 #pragma unroll 1
       for (int n = 0; n < kNU && n < e0.j1 - e0.j0; ++n)
         stage_u(x + 2, e0.j0 + n, (uint32_t)n);
@@ -678,10 +691,6 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
     const bool interior = (t >= 2) && (t < NT - 2) && (col < p.iend);
     const int tma_xq = tma_x0 + item.strip * W - 2;
     const int tma_xu = tma_xq + 2;
-    // last Q row the per-row fast path may stage without looking: beyond it come the ghost rows a
-    // neighbour slab delivers (wait first) and the rows of the next item
-    const int rfast = (!PLAIN && a.kp.edge_hi == EDGE_NEIGHBOUR) ? min(rlast, p.jend - 1) : rlast;
-
     // ghost cells of Q^{n+1} are written by the sweep that produces it: every ghost is a (sign-
     // flipped) copy of ONE domain cell (BoundaryConditions.h:82-147, x and y passes composed), so
     // the thread that owns the source column also stores the ghost columns mirrored from it ...
@@ -769,10 +778,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
           const uint32_t slot = (uint32_t)(n == 0 ? sm1 : s0);
           const int r = rbase + kNS + n;
           if (r <= rlast)
-          {
-            wait_halo_row(r);
             stage_q(tma_xq, r, slot);
-          }
           else
             stage_q_next(r - rlast, slot);
         }
@@ -936,15 +942,10 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
       if (t == 0)
       {
         const uint32_t qslot = (uint32_t)(kDead == 1 ? s1 : (kDead == 0 ? s0 : sm1));
-        if (k + kDead + kNS <= rfast)
+        if (k + kDead + kNS <= rlast)
           stage_q(tma_xq, k + kDead + kNS, qslot);
-        else if (k + kDead + kNS > rlast)
-          stage_q_next(k + kDead + kNS - rlast, qslot);
         else
-        {
-          wait_halo_row(k + kDead + kNS); // (a ghost row that the high neighbour delivers)
-          stage_q(tma_xq, k + kDead + kNS, qslot);
-        }
+          stage_q_next(k + kDead + kNS - rlast, qslot);
         if (k == j1 - 8)
         {
           if (a.persistent)
@@ -1083,14 +1084,14 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
           qo[2] = u4[2] * ir;
           qo[3] = fma(-0.5, fma(u4[2], qo[2], u4[1] * qo[1]), u4[3]) * gm1; // E - (rho u . u) / 2
           // stores the x-ghost copies of this cell (row jt of array `base`, v component v2)
-          auto put_xghosts = [&](double *base, int jt, double v2) {
+          auto put_xghosts = [&](double *base, long long plane, int jt, double v2) {
 #pragma unroll 1
             for (unsigned m = xmask; m != 0; m &= m - 1)
             {
               const int g = __ffs(m) - 1;
-              double *d   = base + L.at(0, (g < Ng) ? g : p.iend + g - Ng, jt);
-              d[0] = qo[0], d[L.plane] = (p.boundary_x == FV2D_BC_REFLECTING) ? -qo[1] : qo[1], d[2 * L.plane] = v2,
-              d[3 * L.plane] = qo[3];
+              double *d   = base + (long long)jt * L.pitch + L.lead + ((g < Ng) ? g : p.iend + g - Ng);
+              d[0] = qo[0], d[plane] = (p.boundary_x == FV2D_BC_REFLECTING) ? -qo[1] : qo[1], d[2 * plane] = v2,
+              d[3 * plane] = qo[3];
             }
           };
           if (final_stage)
@@ -1133,7 +1134,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
           // also store the ghost columns that mirror their column (xmask).  y: the rows within Ng of
           // the slab's edges also go into the ghost rows that mirror them (push_ghost_rows).
           if (xmask != 0)
-            put_xghosts(a.Qout, k, qo[2]);
+            put_xghosts(a.Qout, L.plane, k, qo[2]);
           if (yitem && (k < p.jbeg + Ng || k >= p.jend - Ng))
           {
             // target 0 .. 2Ng-1: this slab's own y-ghost rows at a physical boundary
@@ -1142,7 +1143,8 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
 #pragma unroll 1
             for (int tg = 0; tg < 2 * Ng + 2; ++tg)
             {
-              double *base = a.Qout;
+              double *base    = a.Qout;
+              long long plane = L.plane;
               int jt;
               bool fv = false;
               if (tg < 2 * Ng)
@@ -1158,19 +1160,19 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
               {
                 if (peer_lo == nullptr || k >= p.jbeg + Ng)
                   continue;
-                base = peer_lo, jt = p.Ny + k; // its high ghost rows
+                base = peer_lo, plane = a.peer_lo_plane, jt = a.peer_lo_Ny + k; // its high ghost rows
               }
               else
               {
                 if (peer_hi == nullptr || k < p.jend - Ng)
                   continue;
-                base = peer_hi, jt = k - p.Ny; // its low ghost rows
+                base = peer_hi, plane = a.peer_hi_plane, jt = k - p.Ny; // its low ghost rows
               }
               const double v2 = fv ? -qo[2] : qo[2];
-              double *d       = base + L.at(0, col, jt);
-              d[0] = qo[0], d[L.plane] = qo[1], d[2 * L.plane] = v2, d[3 * L.plane] = qo[3];
+              double *d       = base + (long long)jt * L.pitch + L.lead + col;
+              d[0] = qo[0], d[plane] = qo[1], d[2 * plane] = v2, d[3 * plane] = qo[3];
               if (xmask != 0)
-                put_xghosts(base, jt, v2);
+                put_xghosts(base, plane, jt, v2);
             }
           }
         }
@@ -1297,17 +1299,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
   }
 }
 
-// Development hook (variant builds with -DFV2D_TIMING): per-CTA cycle counts of the last sweep.
-int read_sweep_timing(long long *host, int n)
-{
-#ifdef FV2D_TIMING
-  return cudaMemcpyFromSymbol(host, g_sweep_timing, sizeof(long long) * (size_t)(n < 4096 ? n : 4096)) == cudaSuccess ? 0 : 2;
-#else
-  (void)host, (void)n;
-  return 1;
-#endif
-}
-
+#ifndef FV2D_SOLVER_ONLY
 // --------------------------------------------------------------------------- math probe
 
 // Evaluates the sweep's division-free primitives on arbitrary inputs so that their accuracy is a
@@ -1394,19 +1386,25 @@ void launch_fill_ghosts(const KParams &kp, double *Q, unsigned long long halo_ex
   k_fill_ghosts<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(kp, Q, halo_expected);
 }
 
+#endif // !FV2D_SOLVER_ONLY
+
 // --------------------------------------------------------------------------- dispatch
 
 #ifndef FV2D_NT
 #define FV2D_NT 256
 #endif
 constexpr int kNT = FV2D_NT;
-int sweep_strip_width() { return kNT - 4; }
 
-template <bool PLM, int SOLVER, int GRAV, bool DIFF, bool PLAIN>
+// The 108 instantiations (reconstruction x solver x gravity x diffusion x mode) are compiled in
+// three translation units, one per Riemann solver (-DFV2D_SOLVER_ONLY=<solver>), so that the library
+// builds in parallel; the unit without that macro holds the dispatcher and the small kernels.
+#ifdef FV2D_SOLVER_ONLY
+
+template <bool PLM, int SOLVER, int GRAV, bool DIFF, int MODE>
 static cudaError_t launch_variant(const CUtensorMap &tmQ, const CUtensorMap &tmU, const SweepArgs &a, cudaStream_t s,
                                   bool configure_only)
 {
-  auto kern             = k_sweep<kNT, PLM, SOLVER, GRAV, DIFF, PLAIN>;
+  auto kern             = k_sweep<kNT, PLM, SOLVER, GRAV, DIFF, MODE>;
   constexpr bool FACEC  = !(PLM && SOLVER == FV2D_HLLC);
   constexpr int NS = ring_ns(ring_total(PLM, FACEC, DIFF), ring_dead(PLM, GRAV, DIFF), DIFF);
   constexpr int NU = ring_total(PLM, FACEC, DIFF) - NS;
@@ -1425,12 +1423,18 @@ static cudaError_t launch_one(const CUtensorMap &tmQ, const CUtensorMap &tmU, co
 {
   if (configure_only)
   {
-    cudaError_t e = launch_variant<PLM, SOLVER, GRAV, DIFF, true>(tmQ, tmU, a, s, true);
-    return e != cudaSuccess ? e : launch_variant<PLM, SOLVER, GRAV, DIFF, false>(tmQ, tmU, a, s, true);
+    cudaError_t e = launch_variant<PLM, SOLVER, GRAV, DIFF, kPlain>(tmQ, tmU, a, s, true);
+    if (e == cudaSuccess)
+      e = launch_variant<PLM, SOLVER, GRAV, DIFF, kMulti>(tmQ, tmU, a, s, true);
+    return e != cudaSuccess ? e : launch_variant<PLM, SOLVER, GRAV, DIFF, kGeneral>(tmQ, tmU, a, s, true);
   }
-  const bool plain = a.final_stage && a.U0 == nullptr && a.peer_lo_Qout == nullptr && a.peer_hi_Qout == nullptr;
-  return plain ? launch_variant<PLM, SOLVER, GRAV, DIFF, true>(tmQ, tmU, a, s, false)
-               : launch_variant<PLM, SOLVER, GRAV, DIFF, false>(tmQ, tmU, a, s, false);
+  const bool euler = a.final_stage && a.U0 == nullptr;
+  const bool alone = a.peer_lo_Qout == nullptr && a.peer_hi_Qout == nullptr;
+  if (euler && alone)
+    return launch_variant<PLM, SOLVER, GRAV, DIFF, kPlain>(tmQ, tmU, a, s, false);
+  if (euler)
+    return launch_variant<PLM, SOLVER, GRAV, DIFF, kMulti>(tmQ, tmU, a, s, false);
+  return launch_variant<PLM, SOLVER, GRAV, DIFF, kGeneral>(tmQ, tmU, a, s, false);
 }
 
 template <bool PLM, int SOLVER>
@@ -1448,18 +1452,50 @@ static cudaError_t dispatch2(const CUtensorMap &tmQ, const CUtensorMap &tmU, con
   }
 }
 
-template <bool PLM>
-static cudaError_t dispatch1(const CUtensorMap &tmQ, const CUtensorMap &tmU, const SweepArgs &a, cudaStream_t s, bool cfg,
-                             int solver, int grav, bool diff)
+// entry point of this translation unit's solver
+#define FV2D_CAT2(a, b) a##b
+#define FV2D_ENTRY(n) FV2D_CAT2(sweep_entry_, n)
+cudaError_t FV2D_ENTRY(FV2D_SOLVER_ONLY)(const CUtensorMap &tmQ, const CUtensorMap &tmU, const SweepArgs &a, cudaStream_t s,
+                                         bool cfg, bool plm, int grav, bool diff)
+{
+  return plm ? dispatch2<true, FV2D_SOLVER_ONLY>(tmQ, tmU, a, s, cfg, grav, diff)
+             : dispatch2<false, FV2D_SOLVER_ONLY>(tmQ, tmU, a, s, cfg, grav, diff);
+}
+#define FV2D_TIMING_READER(n) FV2D_CAT2(read_sweep_timing_, n)
+int FV2D_TIMING_READER(FV2D_SOLVER_ONLY)(long long *host, int n)
+{
+#ifdef FV2D_TIMING
+  return cudaMemcpyFromSymbol(host, g_sweep_timing, sizeof(long long) * (size_t)(n < 4096 ? n : 4096)) == cudaSuccess ? 0 : 2;
+#else
+  (void)host, (void)n;
+  return 1;
+#endif
+}
+
+#else // ---- the dispatcher unit
+
+int sweep_strip_width() { return kNT - 4; }
+
+// sweep_entry_<FV2D_HLL | FV2D_HLLC | FV2D_FSLP>: one translation unit each
+cudaError_t sweep_entry_0(const CUtensorMap &, const CUtensorMap &, const SweepArgs &, cudaStream_t, bool, bool, int, bool);
+cudaError_t sweep_entry_1(const CUtensorMap &, const CUtensorMap &, const SweepArgs &, cudaStream_t, bool, bool, int, bool);
+cudaError_t sweep_entry_2(const CUtensorMap &, const CUtensorMap &, const SweepArgs &, cudaStream_t, bool, bool, int, bool);
+int read_sweep_timing_0(long long *, int);
+int read_sweep_timing_1(long long *, int);
+int read_sweep_timing_2(long long *, int);
+static_assert(FV2D_HLL == 0 && FV2D_HLLC == 1 && FV2D_FSLP == 2, "solver enum values name the translation units");
+
+static cudaError_t dispatch_solver(const CUtensorMap &tmQ, const CUtensorMap &tmU, const SweepArgs &a, cudaStream_t s, bool cfg,
+                                   int solver, bool plm, int grav, bool diff)
 {
   switch (solver)
   {
   case FV2D_HLL:
-    return dispatch2<PLM, FV2D_HLL>(tmQ, tmU, a, s, cfg, grav, diff);
+    return sweep_entry_0(tmQ, tmU, a, s, cfg, plm, grav, diff);
   case FV2D_FSLP:
-    return dispatch2<PLM, FV2D_FSLP>(tmQ, tmU, a, s, cfg, grav, diff);
+    return sweep_entry_2(tmQ, tmU, a, s, cfg, plm, grav, diff);
   default:
-    return dispatch2<PLM, FV2D_HLLC>(tmQ, tmU, a, s, cfg, grav, diff);
+    return sweep_entry_1(tmQ, tmU, a, s, cfg, plm, grav, diff);
   }
 }
 
@@ -1471,8 +1507,7 @@ cudaError_t launch_sweep(const CUtensorMap &tmapQ, const CUtensorMap &tmapU, con
   // which the reference applies whatever the gravity mode)
   const int grav  = p.well_balanced_flux_at_y_bc ? 2 : (p.gravity_mode != FV2D_GRAV_NONE ? 1 : 0);
   const bool diff = p.thermal_conductivity_active || p.viscosity_active;
-  return plm ? dispatch1<true>(tmapQ, tmapU, a, s, false, p.riemann_solver, grav, diff)
-             : dispatch1<false>(tmapQ, tmapU, a, s, false, p.riemann_solver, grav, diff);
+  return dispatch_solver(tmapQ, tmapU, a, s, false, p.riemann_solver, plm, grav, diff);
 }
 
 cudaError_t sweep_configure()
@@ -1486,12 +1521,20 @@ cudaError_t sweep_configure()
       for (int grav = 0; grav < 3; ++grav)
         for (int diff = 0; diff < 2; ++diff)
         {
-          cudaError_t e = plm ? dispatch1<true>(dummy, dummy, a, nullptr, true, solver, grav, diff)
-                              : dispatch1<false>(dummy, dummy, a, nullptr, true, solver, grav, diff);
+          cudaError_t e = dispatch_solver(dummy, dummy, a, nullptr, true, solver, plm != 0, grav, diff != 0);
           if (e != cudaSuccess)
             return e;
         }
   return cudaSuccess;
 }
+
+// Development hook (variant builds with -DFV2D_TIMING): per-CTA cycle counts of the last sweep of
+// the given solver's translation unit.
+int read_sweep_timing(int solver, long long *host, int n)
+{
+  return solver == FV2D_HLL ? read_sweep_timing_0(host, n) : (solver == FV2D_FSLP ? read_sweep_timing_2(host, n) : read_sweep_timing_1(host, n));
+}
+
+#endif // FV2D_SOLVER_ONLY
 
 } // namespace fv2d

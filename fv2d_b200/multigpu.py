@@ -15,10 +15,12 @@ from . import capi
 def slab_rows(Ny: int, Ng: int, rank: int, nranks: int):
     """(first local row in the global array incl. ghosts, number of local rows incl. ghosts)
     of y-slab `rank`: owned rows [rank*Ny/nranks, (rank+1)*Ny/nranks) plus Ng ghost rows a side."""
-    if Ny % nranks:
-        raise ValueError("Ny must be divisible by the number of slabs")
-    nyl = Ny // nranks
-    return rank * nyl, nyl + 2 * Ng
+    if Ny < nranks:
+        raise ValueError("more slabs than rows")
+    # rows are dealt out as evenly as they go: the first Ny % nranks slabs get one row more
+    # (fv2d_ctx_create_slab does the same)
+    nyl = Ny // nranks + (1 if rank < Ny % nranks else 0)
+    return rank * (Ny // nranks) + min(rank, Ny % nranks), nyl + 2 * Ng
 
 
 def split_global(Qglobal: np.ndarray, Ng: int, rank: int, nranks: int) -> np.ndarray:

@@ -94,9 +94,9 @@ int fv2d_io_load_snapshot(const fv2d_device_params *dev, const fv2d_run_params *
 int fv2d_ctx_create(const fv2d_device_params *dev, int time_stepping, double eps_reset_negative, int device,
                     fv2d_ctx **out);
 
-/* Multi-GPU variant: this process owns y-slab `rank` of `nranks` (rows
- * [jbeg + rank*Ny/nranks, jbeg + (rank+1)*Ny/nranks) of the global grid described by `dev`;
- * Ny must be divisible by nranks).  Ghost rows at slab interfaces are filled by
+/* Multi-GPU variant: this process owns y-slab `rank` of `nranks` of the global grid described by
+ * `dev`.  The Ny rows are dealt out as evenly as they go (the first Ny % nranks slabs own one row
+ * more); fv2d_ctx_geometry returns the slab's rows and its offset.  Ghost rows at slab interfaces are filled by
  * fv2d_halo_* below instead of the physical y boundary condition. */
 int fv2d_ctx_create_slab(const fv2d_device_params *dev, int time_stepping, double eps_reset_negative, int device,
                          int rank, int nranks, fv2d_ctx **out);

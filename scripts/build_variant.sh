@@ -5,11 +5,9 @@
 set -e
 name=$1; shift
 cd "$(dirname "$0")/.."
-mkdir -p scratch build
-NVCC=/usr/local/cuda/bin/nvcc
-ARCH="-gencode arch=compute_100a,code=sm_100a"
-$NVCC -std=c++17 -O3 $ARCH -lineinfo -Xcompiler -fPIC -Xcudafe --diag_suppress=177 "$@" -Xptxas -v \
-  -c fv2d_b200/csrc/fv2d_sweep.cu -o build/fv2d_sweep_$name.o 2> build/fv2d_sweep_$name.ptxas.log
+mkdir -p scratch build/var_$name
 make -s build/fv2d_ops.o build/fv2d_capi.o
-$NVCC $ARCH -shared -o scratch/lib_$name.so build/fv2d_ops.o build/fv2d_sweep_$name.o build/fv2d_capi.o -cudart static -Xcompiler -fopenmp
-grep -A1 "k_sweepILi[0-9]*ELb1ELi1ELi0ELb0ELb1" build/fv2d_sweep_$name.ptxas.log | grep -E "Used|spill" | tr '\n' ' '; echo
+make -s -j4 OBJDIR=build/var_$name SWEEPFLAGS="$*" build/var_$name/fv2d_sweep.o build/var_$name/fv2d_sweep_s0.o build/var_$name/fv2d_sweep_s1.o build/var_$name/fv2d_sweep_s2.o
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o scratch/lib_$name.so build/fv2d_ops.o build/fv2d_capi.o \
+  build/var_$name/fv2d_sweep.o build/var_$name/fv2d_sweep_s0.o build/var_$name/fv2d_sweep_s1.o build/var_$name/fv2d_sweep_s2.o -cudart static -Xcompiler -fopenmp
+grep -A1 "k_sweepILi[0-9]*ELb1ELi1ELi0ELb0ELi0E" build/var_$name/fv2d_sweep_s1.ptxas.log | grep -E "Used|spill" | tr '\n' ' '; echo

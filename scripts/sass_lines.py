@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Developer tool: attribute the SASS of the k_sweep main loop to source lines.
-   python scripts/sass_lines.py build/fv2d_sweep.o [ILi256ELb1ELi1ELi0ELb0ELb1E]"""
+   python scripts/sass_lines.py build/fv2d_sweep_s1.o [ILi256ELb1ELi1ELi0ELb0ELi0E]"""
 import collections, os, re, subprocess, sys, tempfile
-obj = sys.argv[1] if len(sys.argv) > 1 else "build/fv2d_sweep.o"
-frag = sys.argv[2] if len(sys.argv) > 2 else "ILi256ELb1ELi1ELi0ELb0ELb1E"
+obj = sys.argv[1] if len(sys.argv) > 1 else "build/fv2d_sweep_s1.o"
+frag = sys.argv[2] if len(sys.argv) > 2 else "ILi256ELb1ELi1ELi0ELb0ELi0E"
 d = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=d, capture_output=True)
 cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Developer tool: opcode histogram of the main loop of a k_sweep instantiation.
-#   scripts/sass_loop_hist.sh build/fv2d_sweep.o [mangled-name-fragment]
-obj=${1:-build/fv2d_sweep.o}; frag=${2:-ILi256ELb1ELi1ELi0ELb0ELb1E}
+#   scripts/sass_loop_hist.sh build/fv2d_sweep_s1.o [mangled-name-fragment]
+obj=${1:-build/fv2d_sweep_s1.o}; frag=${2:-ILi256ELb1ELi1ELi0ELb0ELi0E}
 fun=$(cuobjdump -elf $obj 2>/dev/null | grep -o "_ZN4fv2d7k_sweep${frag}[A-Za-z0-9_]*" | sort -u | head -1)
 cuobjdump -sass -fun "$fun" $obj > /tmp/_loop.sass
 # loop = from the target of the last backward BRA.U to that branch

@@ -63,6 +63,9 @@ def test_argument_validation_needs_no_gpu():
     with pytest.raises(capi.Fv2dError) as e:
         capi.Context(bad)
     assert e.value.code == 1 and "B02" in str(e.value)
-    with pytest.raises(capi.Fv2dError) as e:  # Ny not divisible by the number of slabs
-        capi.Context(dev, nranks=3, rank=0)
+    with pytest.raises(capi.Fv2dError) as e:  # 16 rows over 8 slabs: thinner than the two ghost layers
+        capi.Context(dev, nranks=8, rank=0)
+    assert e.value.code == 1 and "thinner" in str(e.value)
+    with pytest.raises(capi.Fv2dError) as e:
+        capi.Context(dev, nranks=9, rank=0)
     assert e.value.code == 1

@@ -3,6 +3,7 @@ path against the reference's own Kokkos-OpenMP binary (oracle/_ref/fv2d_ref, tes
 on identical inputs, 10 steps: relative L1 <= 1e-12 on the conserved fields, dt sequence <= 1e-13,
 domain-integrated mass / energy equal to the reference's to 1e-13 (scripts/parity_fullsize.py has
 the procedure; its record of a run on the B200 box is committed under profiles/)."""
+import os
 import shutil
 import sys
 import tempfile
@@ -21,6 +22,10 @@ pytestmark = pytest.mark.gpu
 def test_fused_path_matches_the_reference_binary_at_full_size(name):
     if not P.REF.exists():
         pytest.skip("oracle/_ref/fv2d_ref not built (dev container: make -C oracle ref)")
+    if name == "rayleigh_taylor_16384" and os.environ.get("FV2D_FULLSIZE_RT") != "1":
+        # the reference needs ~3 minutes of 16 cores for ten 16384^2 steps: opt-in, to keep the default GPU
+        # suite short; profiles/r2_parity_fullsize_vs_reference_binary.json holds the record of a run
+        pytest.skip("set FV2D_FULLSIZE_RT=1 to run the reference on 16384^2 (3 minutes); record in profiles/")
     ram, disk = P.needs(name)
     if P.mem_available_gb() < ram or shutil.disk_usage(tempfile.gettempdir()).free / 1e9 < disk:
         pytest.skip(f"needs {ram:.0f} GB host RAM and {disk:.0f} GB scratch")

@@ -45,6 +45,28 @@ def test_baseline_md_anchors():
     assert list(g.dts[:3]) == [0.00096824586252223176, 0.0009498801116487283, 0.00088692715039051105]
 
 
+def test_baseline_md_anchors_kh_256():
+    """BASELINE.md §6, second row of anchors: Kelvin-Helmholtz 256^2 PLM, dt0 / dt9 and the
+    domain sums after 10 steps, as the survey recorded them from the reference build.  The oracle is
+    bit-identical to the reference on every fixture, so it must land on the same digits (the sums are
+    accumulated sequentially like the survey's driver did; a last-digit difference of the summation
+    order is allowed for)."""
+    dev, run = capi.params_from_ini(load_golden("kh_plm_128x64").ini_path(), {"mesh.Nx": 256, "mesh.Ny": 256})
+    Q = capi.init_problem(dev, run)
+    U = O.prim_to_cons(dev, Q)
+    n, t, dts, neg = O.run(dev, run.time_stepping, run.epsilon_reset_negative, run.tend, Q, U, 10)
+    assert n == 10 and neg == [0, 0, 0]
+    assert dts[0] == 0.00094323644991366196 and dts[9] == 0.00094313650081637775
+    UN = O.domain(dev, U)
+    mass, energy = 0.0, 0.0
+    for v in UN[0].ravel():
+        mass += v * dev.dx * dev.dy
+    for v in UN[3].ravel():
+        energy += v * dev.dx * dev.dy
+    assert abs(mass - 11.999999999586402) <= 2e-15 * 12.0
+    assert abs(energy - 125.40006088566672) <= 2e-15 * 125.4
+
+
 def test_sod_x_y_symmetry():
     """sod_y is sod_x transposed with u<->v (SURVEY.md §4 known-answer check)."""
     gx, gy = load_golden("sod_x"), load_golden("sod_y")

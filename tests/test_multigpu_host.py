@@ -17,20 +17,24 @@ def test_slab_rows_and_split_join_roundtrip():
     Ng, Ny, Ntx = 2, 24, 11
     rng = np.random.default_rng(0)
     Q = rng.normal(size=(4, Ny + 2 * Ng, Ntx))
-    for n in (1, 2, 3, 4, 8):
+    for n in (1, 2, 3, 4, 5, 7, 8):  # 24 rows over 5 or 7 slabs: uneven (the first Ny % n slabs own one row more)
         slabs = [multigpu.split_global(Q, Ng, r, n) for r in range(n)]
-        nyl = Ny // n
+        owned, first = [], 0
         for r, s in enumerate(slabs):
             j0, rows = multigpu.slab_rows(Ny, Ng, r, n)
-            assert (j0, rows) == (r * nyl, nyl + 2 * Ng) and s.shape == (4, rows, Ntx)
+            nyl = Ny // n + (1 if r < Ny % n else 0)
+            assert (j0, rows) == (first, nyl + 2 * Ng) and s.shape == (4, rows, Ntx)
+            first += nyl
+            owned.append(nyl)
             # a slab's ghost rows are its neighbours' edge rows
             if r > 0:
                 assert np.array_equal(s[:, :Ng], slabs[r - 1][:, -2 * Ng:-Ng])
             if r < n - 1:
                 assert np.array_equal(s[:, -Ng:], slabs[r + 1][:, Ng:2 * Ng])
+        assert sum(owned) == Ny and max(owned) - min(owned) <= 1
         assert np.array_equal(multigpu.join_slabs(slabs, Ng), Q)
     with pytest.raises(ValueError):
-        multigpu.slab_rows(25, 2, 0, 2)
+        multigpu.slab_rows(3, 2, 0, 4)
 
 
 def _free_port():
