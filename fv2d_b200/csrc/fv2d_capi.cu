@@ -75,7 +75,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_tmap(CUtensorMap *out, double *base, const Layout &L, int box_cols)
+static int make_tmap(CUtensorMap *out, double *base, const Layout &L, int box_cols, int ncols = 0)
 {
   static PFN_encodeTiled fn = nullptr;
   if (!fn)
@@ -91,7 +91,9 @@ static int make_tmap(CUtensorMap *out, double *base, const Layout &L, int box_co
     fn = (PFN_encodeTiled)p;
   }
   // 3-D tensor: (column, row, field), fp64, row pitch and plane stride in bytes
-  cuuint64_t dims[3]    = {(cuuint64_t)L.pitch, (cuuint64_t)L.rows, 4};
+  // (ncols: a store descriptor is cut off after the last domain column, so that the box of the
+  // last strip does not write the ghost columns and the padding behind it)
+  cuuint64_t dims[3]    = {(cuuint64_t)(ncols ? ncols : L.pitch), (cuuint64_t)L.rows, 4};
   cuuint64_t strides[2] = {(cuuint64_t)L.pitch * sizeof(double), (cuuint64_t)L.plane * sizeof(double)};
   cuuint32_t box[3]     = {(cuuint32_t)box_cols, 1, 4};
   cuuint32_t estr[3]    = {1, 1, 1};
@@ -224,6 +226,20 @@ static int ensure_slopes(fv2d_ctx *c)
   FV2D_CUDA(cudaMemsetAsync(c->slopesY, 0, bytes, c->stream));
   return FV2D_OK;
 }
+// device copy of the store descriptor of U (slot 0) or Ustar (slot 1)
+static int upload_store_tmap(fv2d_ctx *c, int slot, double *base)
+{
+  CUtensorMap m;
+  int rc = make_tmap(&m, base, c->kp.L, sweep_strip_width(), c->kp.L.lead + c->kp.p.iend);
+  if (rc)
+    return rc;
+  if (!c->tmaps_dev)
+    FV2D_CUDA(cudaMalloc(&c->tmaps_dev, 2 * sizeof(CUtensorMap)));
+  FV2D_CUDA(cudaMemcpyAsync(c->tmaps_dev + slot, &m, sizeof m, cudaMemcpyHostToDevice, c->stream));
+  FV2D_CUDA(cudaStreamSynchronize(c->stream));
+  return FV2D_OK;
+}
+
 static int ensure_ustar(fv2d_ctx *c)
 {
   if (c->Ustar)
@@ -231,7 +247,8 @@ static int ensure_ustar(fv2d_ctx *c)
   const size_t bytes = array_bytes(c->kp.L);
   FV2D_CUDA(cudaMalloc(&c->Ustar, bytes));
   FV2D_CUDA(cudaMemsetAsync(c->Ustar, 0, bytes, c->stream));
-  return make_tmap(&c->tmapUstar, c->Ustar, c->kp.L, sweep_strip_width());
+  int rc = upload_store_tmap(c, 1, c->Ustar);
+  return rc ? rc : make_tmap(&c->tmapUstar, c->Ustar, c->kp.L, sweep_strip_width());
 }
 
 // Update.h:176-191 with the operator-level kernels
@@ -416,6 +433,7 @@ static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
       return rc;
     // stage 1: U* = U + dt L(Q), Q* = consToPrim(U*)           (Update.h:204-210)
     a.Uin = c->U, a.Uout = c->Ustar, a.U0 = nullptr, a.Qout = c->Q[nxt], a.final_stage = 0;
+    a.tm_store_u = c->tmaps_dev + 1;
     set_peers(nxt);
     prof_mark(0);
     e = launch_sweep(c->tmapQ[cur], c->tmapU, a, c->stream);
@@ -428,6 +446,7 @@ static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
       fill_ghosts(c->Q[nxt]);
     // stage 2: U = 0.5 (U0 + U* + dt L(Q*)), Q = consToPrim(U)    (Update.h:211-220, main.cpp:80-81)
     a.Uin = c->Ustar, a.Uout = c->U, a.U0 = c->U, a.Qout = c->Q[cur], a.final_stage = 1;
+    a.tm_store_u = c->tmaps_dev;
     set_peers(cur);
     prof_mark(0);
     e = launch_sweep(c->tmapQ[nxt], c->tmapUstar, a, c->stream);
@@ -439,6 +458,7 @@ static int fused_step(fv2d_ctx *c, bool device_dt, double dt_host)
   else
   {
     a.Uin = c->U, a.Uout = c->U, a.U0 = nullptr, a.Qout = c->Q[nxt], a.final_stage = 1;
+    a.tm_store_u = c->tmaps_dev;
     set_peers(nxt);
     prof_mark(0);
     e = launch_sweep(c->tmapQ[cur], c->tmapU, a, c->stream);
@@ -770,6 +790,8 @@ int fv2d_ctx_create_slab(const fv2d_device_params *dev, int time_stepping, doubl
                (make_tmap(&c->tmapU, c->U, L, sweep_strip_width()) == FV2D_OK);
   if (!c->tmap_ok)
     return fail(FV2D_ERR_CUDA);
+  if ((rc = upload_store_tmap(c, 0, c->U)))
+    return fail(rc);
   if ((rc = build_work_items(c)))
     return fail(rc);
   // The sweep writes the ghost cells of its own output when every ghost mirrors a DOMAIN cell
@@ -804,6 +826,7 @@ void fv2d_ctx_destroy(fv2d_ctx *c)
   cudaFree(c->slopesY);
   cudaFree(c->gtab);
   cudaFree(c->items_dev);
+  cudaFree(c->tmaps_dev);
   cudaFree(c->rowsum);
   cudaFree(c->sc);
   if (c->prof_ev)

@@ -220,6 +220,7 @@ struct fv2d_ctx
 
   CUtensorMap tmapQ[2]; // TMA descriptors of Q[0], Q[1]
   CUtensorMap tmapU, tmapUstar; // ... of U and of the RK2 stage array (valid once Ustar exists)
+  CUtensorMap *tmaps_dev; // device copies of the store descriptors: [0] U, [1] Ustar
   bool tmap_ok;
   // persistent sweep: work-item table (device), its length, grid size
   fv2d::WorkItem *items_dev;

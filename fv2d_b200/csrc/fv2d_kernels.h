@@ -47,6 +47,8 @@ struct SweepArgs
   int fold_ghosts;   // 1: the epilogue also writes the ghost cells of Qout (boundary conditions)
   int n_ctas;        // grid size = min(n_items, resident CTA slots); = n_items when !persistent
   int persistent;    // 1: CTAs pull further items from the device-wide counter (every item has >= 8 rows)
+  const CUtensorMap *tm_store_u; // device copy of the TMA descriptor the stage STORES Uout rows through (columns
+                                 // beyond the domain clipped)
   const WorkItem *items; // device table, n_items entries + the end marker
   int n_items;
   // multi-GPU: the neighbours' copy of Qout (peer-mapped), or nullptr at a physical edge.  The

@@ -75,6 +75,22 @@ __device__ __forceinline__ void tma_load_3d_u32(uint32_t dst, const CUtensorMap 
                : "memory");
 }
 
+// TMA store (shared -> 3-D tensor map, bulk async-group completion) and its bookkeeping
+__device__ __forceinline__ void tma_store_3d_u32(const CUtensorMap *tmap, uint32_t src, int x, int y, int z)
+{
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap), "r"(src), "r"(x),
+               "r"(y), "r"(z)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read()
+{
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// makes this thread's earlier shared-memory writes visible to the async proxy (TMA store source)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // 16-byte asynchronous copy global -> shared (a work-table entry), and its completion wait
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src)
 {
@@ -109,6 +125,9 @@ __device__ __forceinline__ int bc_src(int bc, int k, int beg, int end, int N)
 #endif
 #ifndef FV2D_PS_SHORT
 #define FV2D_PS_SHORT 1
+#endif
+#ifndef FV2D_TMA_STORE_U
+#define FV2D_TMA_STORE_U 1 // U^{n+1} rows leave through the ring slot U^n arrived in, by TMA store
 #endif
 #ifndef FV2D_HLLC_UNIFORM
 #define FV2D_HLLC_UNIFORM 0 // 1: select-free HLLC tail when a whole warp takes the same branch (measured slower)
@@ -532,6 +551,14 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
     tma_load_3d_u32(urng0 + kQRowBytes * slot, &tmU, x, r, 0, ubar0 + 8u * slot);
   };
 
+  // U^{n+1} of a row is written back into the ring slot its U^n arrived in (same dense [field][W] box,
+  // every thread its own element) and leaves through a TMA store one iteration later; the slot is
+  // re-armed for the next load one iteration after that, when the store has read it.
+  auto store_u = [&](int x, int r, uint32_t slot) {
+    tma_store_3d_u32(a.tm_store_u, urng0 + kQRowBytes * slot, x, r, 0);
+    bulk_commit();
+  };
+
   // ---- work queue (thread 0).  A CTA always knows its current item and the next one (the rows of
   // the next item are staged while the current one finishes).  The item after those is taken from
   // the device-wide counter as LATE as possible - 8 rows before the current item ends - because an
@@ -670,7 +697,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
   // parity of the next Q row of the stream, (us, uph) = ... of the next U row
   int s2 = 0, s1 = 0, s0 = 0, sm1 = 0;
   uint32_t ph2 = 0;
-  int us = 0, us_prev = 0;
+  int us = 0, us_prev = 0, us_prev2 = 0;
   uint32_t uph = 0;
   auto next_q = [&]() {
     s2 = (s2 + 1 == kNS) ? 0 : s2 + 1;
@@ -956,6 +983,20 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
           if (a.persistent)
             cp_async_16(smem_u32(&S.item_in), a.items + min(pend, (unsigned)a.n_items));
         }
+#if FV2D_TMA_STORE_U
+        if (k > j0)
+        {
+          store_u(tma_xu, k - 1, (uint32_t)us_prev); // U^{n+1} of row k-1: every thread wrote it before the barrier
+          if (k > j0 + 1)
+          {
+            bulk_wait_read<1>(); // the store of row k-2 (issued one iteration ago) has read its slot
+            if (k - 2 + kNU < j1)
+              stage_u(tma_xu, k - 2 + kNU, (uint32_t)us_prev2);
+            else
+              stage_u_next(k - 2 + kNU - j1, (uint32_t)us_prev2);
+          }
+        }
+#else
         if (k > j0)
         {
           if (k - 1 + kNU < j1)
@@ -963,6 +1004,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
           else
             stage_u_next(k - 1 + kNU - j1, (uint32_t)us_prev);
         }
+#endif
       }
 
       // D. finish row k
@@ -1072,9 +1114,19 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
             for (int f = 0; f < 4; ++f)
               u4[f] = 0.5 * (FV2D_CAT(U0, f) + u4[f]);
           }
+#if FV2D_TMA_STORE_U
+          {
+            double *ub = &S.uring[us][0][0];
+#pragma unroll
+            for (int f = 0; f < 4; ++f)
+              ub[f * W + tu] = u4[f];
+            fence_proxy_async_smem();
+          }
+#else
 #pragma unroll
           for (int f = 0; f < 4; ++f)
             FV2D_AT(a.Uout, f) = u4[f];
+#endif
 
           // consToPrim (States.h:32-43)
           const double ir = frcp(u4[0]);
@@ -1199,7 +1251,8 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
         qn[f] = qnn[f];
       sm1 = s0, s0 = s1, s1 = s2;
       next_q();
-      us_prev = us;
+      us_prev2 = us_prev;
+      us_prev  = us;
       us = (us + 1 == kNU) ? 0 : us + 1;
       uph ^= (us == 0) ? 1u : 0u;
     }
@@ -1236,7 +1289,18 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
 #pragma unroll 1
       for (int n = 2 + kDead; n <= 3; ++n)
         stage_q_next(n + kNS - 3, (uint32_t)(n == 1 ? sm1 : (n == 2 ? s0 : s1)));
+#if FV2D_TMA_STORE_U
+      store_u(tma_xu, j1 - 1, (uint32_t)us_prev); // the item's last row
+      if (nrow >= 2)
+      {
+        bulk_wait_read<1>();
+        stage_u_next(kNU - 2, (uint32_t)us_prev2);
+      }
+      bulk_wait_read<0>();
       stage_u_next(kNU - 1, (uint32_t)us_prev);
+#else
+      stage_u_next(kNU - 1, (uint32_t)us_prev);
+#endif
       // the next item becomes the current one; the entry that landed in item_in is the one after it
       cp_async_wait_all();
       const WorkItem e2 = S.item_in;
