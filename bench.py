@@ -211,6 +211,7 @@ class Job:
         import torch
 
         env, ctx = self.env, self.ctx
+        ctx.sync_wait(reset=True)
         ctx.profile_enable(True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         env.barrier()
@@ -222,6 +223,9 @@ class Job:
         ms = env.max_over_ranks(e0.elapsed_time(e1))
         sweep_ms, sweep_launches, total_launches = ctx.profile_read()
         ctx.profile_enable(False)
+        # per-step wait of this rank's first CTA for the other ranks' CFL mails (the decomposition's
+        # synchronisation cost; 0 on one GPU), maximum over the ranks
+        self.cfl_wait_us = env.max_over_ranks(ctx.sync_wait()[1] / max(sweep_launches, 1))
         return ms, sweep_ms, sweep_launches, total_launches
 
     def global_hash(self):
@@ -318,6 +322,7 @@ def native_arm(args):
     for _ in range(max(1, args.reps)):
         reps.append(job.timed(args.steps))
     clocks = sampler.stop() if rank == 0 else None
+    cfl_wait_main = job.cfl_wait_us
     order = sorted(range(len(reps)), key=lambda k: reps[k][0])
     ms, sweep_ms, sweep_launches, total_launches = reps[order[len(order) // 2]]
     value = Nx * Ny * args.steps / (ms * 1e-3) / 1e6
@@ -401,7 +406,7 @@ def native_arm(args):
         pl, ach, fr = j.roofline(b_sweep_ms, b_launches, peak)
         out = {"workload": workload, "Nx": j.Nx, "Ny": j.Ny, "scaling": scaling, "steps": steps,
                "value": j.Nx * j.Ny * steps / (b_ms * 1e-3) / 1e6, "unit": "Mcell-updates/s", "ms_per_step": b_ms / steps,
-               "frac": fr, "ms_per_launch": pl * 1e3, "state_hash": None}
+               "frac": fr, "ms_per_launch": pl * 1e3, "cfl_mail_wait_us_per_step": j.cfl_wait_us}
         j.close()
         return out
 
@@ -439,7 +444,8 @@ def native_arm(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": frac,
                          "traffic": traffic, "kernel": "k_sweep (fused RK stage, persistent)", "peak_source": peak_src,
                          "bytes_per_cell_update": BYTES_PER_CELL_UPDATE, "ms_per_launch": per_launch_s * 1e3,
-                         "share_of_step": sweep_ms / ms if ms > 0 else None, "fp64": fp64},
+                         "share_of_step": sweep_ms / ms if ms > 0 else None, "fp64": fp64,
+                         "cfl_mail_wait_us_per_step": cfl_wait_main},
             "sustained": sustained, "state_hash": {"after_steps": HASH_STEPS, "u64": f"0x{state_hash:016x}"},
             "strong_16384": strong_16384, "weak": weak,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(total_launches), "clocks": clocks,

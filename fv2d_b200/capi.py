@@ -193,6 +193,7 @@ def lib() -> C.CDLL:
         "fv2d_state_hash": [_ctxp, C.POINTER(C.c_uint64)],
         "fv2d_debug_fp64_peak": [C.c_int, _dp],
         "fv2d_debug_sweep_timing": [_ctxp, C.POINTER(C.c_int64), C.c_int],
+        "fv2d_debug_sync_wait": [_ctxp, _dp, _dp, _dp, C.c_int],
         "fv2d_debug_schedule": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int)],
     }
     for name, argtypes in sig.items():
@@ -446,6 +447,13 @@ class Context:
         out = np.zeros((n_ctas, 4), dtype=np.int64)
         _check(lib().fv2d_debug_sweep_timing(self._h, out.ctypes.data_as(C.POINTER(C.c_int64)), 4 * n_ctas))
         return out
+
+    def sync_wait(self, reset: bool = False):
+        """(wait for the other ranks' CFL mails in the last sweep, accumulated wait since the last reset,
+        busy time of the last sweep), microseconds."""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        _check(lib().fv2d_debug_sync_wait(self._h, C.byref(a), C.byref(b), C.byref(c), int(reset)))
+        return a.value, b.value, c.value
 
     def halo_export(self) -> bytes:
         buf = C.create_string_buffer(FV2D_IPC_HANDLE_BYTES)

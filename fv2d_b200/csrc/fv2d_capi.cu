@@ -309,6 +309,8 @@ static std::vector<std::pair<int, int>> schedule_runs(int Ny, int nstrips, int s
   const int runs_per_round = std::max(1, (slots + nstrips / 2) / nstrips);
   std::vector<std::pair<int, int>> runs;
   int lo = 0, hi = Ny;
+  if (std::getenv("FV2D_FORCE_EDGE_RUNS")) // development: the schedule of a slab with neighbours
+    nb_lo = nb_hi = true;
   if (nb_lo && hi - lo >= 2 * hmin)
   {
     runs.emplace_back(lo, lo + hmin);
@@ -1209,6 +1211,27 @@ int fv2d_state_hash(fv2d_ctx *c, uint64_t *hash)
   if (rc)
     return rc;
   *hash = c->sc_host->hash;
+  return FV2D_OK;
+}
+
+int fv2d_debug_sync_wait(fv2d_ctx *c, double *last_wait_us, double *total_wait_us, double *last_busy_us, int reset)
+{
+  FV2D_ENTER(c);
+  int rc = read_scalars(c);
+  if (rc)
+    return rc;
+  const unsigned long long *ts = c->sc_host->tstamp;
+  if (last_wait_us)
+    *last_wait_us = (double)(ts[1] - ts[0]) * 1e-3;
+  if (total_wait_us)
+    *total_wait_us = (double)ts[3] * 1e-3;
+  if (last_busy_us)
+    *last_busy_us = (double)(ts[2] - ts[1]) * 1e-3;
+  if (reset)
+  {
+    FV2D_CUDA(cudaMemsetAsync(&c->sc->tstamp[3], 0, sizeof(unsigned long long), c->stream));
+    return sync_ctx(c);
+  }
   return FV2D_OK;
 }
 

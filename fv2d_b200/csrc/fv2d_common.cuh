@@ -61,6 +61,8 @@ struct DevScalars
   double inv_dt_last[4];            // decoded maxima behind `dt`
   double sums[2];                   // scratch for mass/energy integration
   unsigned long long hash;          // scratch for fv2d_state_hash
+  unsigned long long tstamp[4];     // %globaltimer (ns) of the last sweep: CTA 0 started, CTA 0 had its dt (all CFL
+                                    // mails in), last CTA done; [3] = accumulated wait for the mails since reset
   // ---- multi-GPU mailboxes: written by peers over NVLink (system-scope stores), read locally
   unsigned long long halo_cnt[2];      // ghost-row pushes received from the low-j / high-j neighbour
   unsigned long long mail_gen[kMaxRanks]; // per source rank: generation of its last CFL mail
@@ -158,15 +160,29 @@ __device__ __forceinline__ bool wait_ge_sys(const unsigned long long *p, unsigne
   return true;
 }
 
-// Posts this rank's maximum inverse time-step to every rank's mailbox (self included) and
-// stamps it with generation `gen`.  Called by exactly one thread per reduction.
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v)
+{
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Posts this rank's maximum inverse time-step to rank q's mailbox and stamps it with generation
+// `gen`: value, system-scope fence, generation (the fence-release pattern: one NVLink round trip).
+// The sweep calls it from lanes 0 .. nranks-1 of one warp, so that all mailboxes are written at
+// once: eight release stores issued one after the other by a single thread cost eight round trips,
+// on the critical path of every rank's next step.
+__device__ __forceinline__ void post_cfl_mail_to(const KParams &kp, int q, double hyp, unsigned long long gen)
+{
+  st_relaxed_sys_f64(&kp.peer_sc[q]->mail_inv[gen & 1][kp.rank], hyp);
+  __threadfence_system();
+  st_relaxed_sys_u64(&kp.peer_sc[q]->mail_gen[kp.rank], gen);
+}
+// ... to every rank's mailbox (self included), by one thread (the stand-alone computeDt).
 __device__ __forceinline__ void post_cfl_mail(const KParams &kp, double hyp, unsigned long long gen)
 {
   for (int q = 0; q < kp.nranks; ++q)
     st_relaxed_sys_f64(&kp.peer_sc[q]->mail_inv[gen & 1][kp.rank], hyp);
   __threadfence_system();
   for (int q = 0; q < kp.nranks; ++q)
-    st_release_sys(&kp.peer_sc[q]->mail_gen[kp.rank], gen);
+    st_relaxed_sys_u64(&kp.peer_sc[q]->mail_gen[kp.rank], gen);
 }
 // Waits for generation `gen` of every rank's mail and returns the global maximum.
 __device__ __forceinline__ double collect_cfl_mail(const KParams &kp, unsigned long long gen)

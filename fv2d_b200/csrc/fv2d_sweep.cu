@@ -35,6 +35,7 @@
 // epilogue of the rows they mirror, and the clock (t += dt) is advanced by the sweep's last CTA.
 #include "fv2d_kernels.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
@@ -570,10 +571,16 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
   // over NVLink).  Before the first row of an item that reads such rows is staged, wait for all of
   // them, then order those writes before the async-proxy reads of TMA.  (After a final-stage sweep
   // the wait never spins: the CFL mail this sweep has already received is posted after the
-  // neighbour's last push.  It does between the two stages of an RK2 step.)  Called when an item is
-  // published as the next one, outside the row loop.
+  // neighbour's last push.  It does between the two stages of an RK2 step.)  Executed by ALL threads
+  // of the CTA on a CTA-uniform condition: a spin loop under `if (t == 0)` anywhere inside the item
+  // loop makes ptxas move the ring bookkeeping of the whole kernel from uniform to vector registers
+  // (measured: +36 IMAD and 19 R2UR per row, the kMulti sweep 3.7 % slower than kPlain).
   auto wait_halo_item = [&](const WorkItem &e) {
+#ifndef FV2D_X_NOWAIT
     if constexpr (!PLAIN)
+#else
+    if constexpr (false)
+#endif
     {
       if (e.j0 < 0)
         return;
@@ -600,7 +607,6 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
       stage_u(S.nx_xq + 2, r, slot);
   };
   auto publish_next = [&](const WorkItem &e) { // thread 0: e is the item after the current one
-    wait_halo_item(e);
     S.nx_xq    = tma_x0 + e.strip * W - 2;
     S.nx_rbase = e.j0 - 2;
     S.nx_rlast = (e.j0 < 0) ? e.j0 - 3 : e.j1 + 1;
@@ -608,7 +614,10 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
     S.nx_j1    = e.j1;
   };
 
-  // ---- kernel prologue (thread 0): barriers, the first three work items, the initial fill of both
+  if constexpr (!PLAIN)
+    wait_halo_item(a.items[blockIdx.x]); // the CTA's first item (all threads: see wait_halo_item)
+
+  // ---- kernel prologue (thread 0): barriers, the first two work items, the initial fill of both
   // rings, and this step's dt
   if (t == 0)
   {
@@ -629,7 +638,6 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
     S.item_in = WorkItem{0, -1, -1, 0};
     const WorkItem e1 = a.items[i1]; // items[n_items] is the end marker
     S.item[0] = e0, S.item[1] = e1;
-    wait_halo_item(e0);
     publish_next(e1);
     // initial fill of both rings from the first item (>= 8 rows unless it is the CTA's only one)
     {
@@ -644,6 +652,9 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
     // dt = CFL / max(inverse time-steps of the current state)   (ComputeDt.h:64): the hyperbolic
     // maximum was mailed to every rank by the last CTA of the previous final-stage sweep
     double dt = a.dt_host, hyp = 0.0, tc = p.epsilon, visc = p.epsilon;
+    unsigned long long tg0 = 0, tg1 = 0;
+    if (blockIdx.x == 0)
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tg0));
     if (a.use_device_dt)
     {
       hyp = collect_cfl_mail(a.kp, a.mail_gen);
@@ -659,6 +670,13 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
       dt = p.CFL / m;
       if (sc->fault) // a wait on a peer timed out: stop advancing (the host reports the fault)
         dt = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    if (blockIdx.x == 0)
+    {
+      // how long this rank waited for the other ranks' CFL mails (0 on a single slab): the per-step
+      // synchronisation cost of the y-slab decomposition, reported by bench.py
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tg1));
+      sc->tstamp[0] = tg0, sc->tstamp[1] = tg1, sc->tstamp[3] += tg1 - tg0;
     }
     S.dt      = dt;
     S.inv3[0] = hyp, S.inv3[1] = tc, S.inv3[2] = visc;
@@ -709,6 +727,10 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
     const WorkItem item = S.item[ci & 1];
     if (item.j0 < 0)
       break;
+    if constexpr (!PLAIN)
+      wait_halo_item(S.item[(ci + 1) & 1]); // the rows of the next item are staged while this one finishes
+    // (thread 0, which does the staging, wrote that entry itself; a thread that still sees the slot's
+    //  previous content waits for nothing it needs)
     const int j0 = item.j0, j1 = item.j1; // rows [j0, j1) are updated
     const int i0    = p.ibeg + item.strip * W; // first interior column of the strip
     const int col   = i0 - 2 + t;              // this thread's column
@@ -1267,7 +1289,11 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
     // thread is done with them their slots move on down the stream.  Multi-GPU: tell the neighbours
     // how many of their ghost rows this item has delivered.
     int n_lo = 0, n_hi = 0;
+#ifndef FV2D_X_NOCOUNT
     if constexpr (!PLAIN)
+#else
+    if constexpr (false)
+#endif
     {
       n_lo = (peer_lo != nullptr) ? max(0, min(j1, p.jbeg + Ng) - j0) : 0;
       n_hi = (peer_hi != nullptr) ? max(0, j1 - max(j0, p.jend - Ng)) : 0;
@@ -1331,27 +1357,42 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
     g_sweep_timing[blockIdx.x * 4 + 3] = now - tm_start;
   }
 #endif
-  if (t == 0)
+  if (t < 32)
   {
-    if (final_stage)
+    int last = 0;
+    double hyp_slab = 0.0;
+    if (t == 0)
     {
-      double m = red[0];
-      for (int w = 1; w < NT / 32; ++w)
-        m = fmax(m, red[w]);
-      atomicMax(&sc->inv_acc[1][0], encode_ordered(m));
-    }
-    __threadfence();
-    const unsigned prev = atomicAdd(&sc->cta_done, 1u);
-    if (prev == gridDim.x - 1)
-    {
-      sc->cta_done  = 0;
-      sc->work_next = 0;
       if (final_stage)
       {
-        // the slab's maximum goes to every rank's mailbox (self included): the next step's dt is
-        // reduced on the device, no host round trip.  Then the device-side clock (main.cpp:83).
-        const unsigned long long enc = atomicExch(&sc->inv_acc[1][0], FV2D_ENC_NEG_MAX);
-        post_cfl_mail(a.kp, decode_ordered(enc), a.mail_gen + 1);
+        double m = red[0];
+        for (int w = 1; w < NT / 32; ++w)
+          m = fmax(m, red[w]);
+        atomicMax(&sc->inv_acc[1][0], encode_ordered(m));
+      }
+      __threadfence();
+      const unsigned prev = atomicAdd(&sc->cta_done, 1u);
+      if (prev == gridDim.x - 1)
+      {
+        last          = 1;
+        sc->cta_done  = 0;
+        sc->work_next = 0;
+        if (final_stage)
+          hyp_slab = decode_ordered(atomicExch(&sc->inv_acc[1][0], FV2D_ENC_NEG_MAX));
+      }
+    }
+    last     = __shfl_sync(0xffffffffu, last, 0);
+    hyp_slab = __shfl_sync(0xffffffffu, hyp_slab, 0);
+    if (last && final_stage)
+    {
+      // The sweep's last CTA: the slab's maximum goes to every rank's mailbox (self included), one
+      // lane per rank - the next step's dt is reduced on the device, no host round trip.  Then the
+      // device-side clock (main.cpp:83).
+      if (t < a.kp.nranks)
+        post_cfl_mail_to(a.kp, t, hyp_slab, a.mail_gen + 1);
+      if (t == 0)
+      {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(sc->tstamp[2]));
         sc->dt                                  = dt;
         sc->dt_hist[sc->step % FV2D_DT_HISTORY] = dt;
         sc->t += dt;
@@ -1485,6 +1526,9 @@ template <bool PLM, int SOLVER, int GRAV, bool DIFF>
 static cudaError_t launch_one(const CUtensorMap &tmQ, const CUtensorMap &tmU, const SweepArgs &a, cudaStream_t s,
                               bool configure_only)
 {
+#ifdef FV2D_ONLY_MODE // development: compile a single mode
+  return launch_variant<PLM, SOLVER, GRAV, DIFF, FV2D_ONLY_MODE>(tmQ, tmU, a, s, configure_only);
+#endif
   if (configure_only)
   {
     cudaError_t e = launch_variant<PLM, SOLVER, GRAV, DIFF, kPlain>(tmQ, tmU, a, s, true);
@@ -1493,7 +1537,10 @@ static cudaError_t launch_one(const CUtensorMap &tmQ, const CUtensorMap &tmU, co
     return e != cudaSuccess ? e : launch_variant<PLM, SOLVER, GRAV, DIFF, kGeneral>(tmQ, tmU, a, s, true);
   }
   const bool euler = a.final_stage && a.U0 == nullptr;
-  const bool alone = a.peer_lo_Qout == nullptr && a.peer_hi_Qout == nullptr;
+  static const int force_mode = std::getenv("FV2D_FORCE_MODE") ? std::atoi(std::getenv("FV2D_FORCE_MODE")) : 0; // development
+  const bool alone = a.peer_lo_Qout == nullptr && a.peer_hi_Qout == nullptr && force_mode < 1;
+  if (force_mode >= 2)
+    return launch_variant<PLM, SOLVER, GRAV, DIFF, kGeneral>(tmQ, tmU, a, s, false);
   if (euler && alone)
     return launch_variant<PLM, SOLVER, GRAV, DIFF, kPlain>(tmQ, tmU, a, s, false);
   if (euler)
@@ -1505,6 +1552,11 @@ template <bool PLM, int SOLVER>
 static cudaError_t dispatch2(const CUtensorMap &tmQ, const CUtensorMap &tmU, const SweepArgs &a, cudaStream_t s, bool cfg,
                              int grav, bool diff)
 {
+#ifdef FV2D_ONLY_ONE // development: compile a single (reconstruction, gravity, diffusion) combination
+  if (PLM)
+    return launch_one<true, SOLVER, 0, false>(tmQ, tmU, a, s, cfg);
+  return cudaErrorInvalidValue;
+#endif
   switch (grav)
   {
   case 0:

@@ -200,6 +200,12 @@ int fv2d_debug_math_probe(int device, int64_t n, const double *a, const double *
  * denominator of the second roofline (FP64-pipe utilisation) bench.py reports. */
 int fv2d_debug_fp64_peak(int device, double *dfma_per_second);
 
+/* Measurement hook: what the y-slab decomposition costs per step in synchronisation.  Every sweep's
+ * first CTA notes how long it waited for the other ranks' CFL mails before it had its dt.
+ * last_wait_us: that wait in the last sweep; total_wait_us: accumulated since the last reset;
+ * last_busy_us: from dt available to the last CTA done, last sweep.  (Any pointer may be NULL.) */
+int fv2d_debug_sync_wait(fv2d_ctx *ctx, double *last_wait_us, double *total_wait_us, double *last_busy_us, int reset);
+
 /* Test hook (host only, needs no GPU): the row runs [first, last) - relative to the first domain row
  * of the slab - into which the persistent sweep cuts a slab of Nx x Ny_local cells on a device with
  * num_sms SMs, in table order (every run is crossed with every strip of 252 columns to give the work
