@@ -358,6 +358,9 @@ static int build_work_items(fv2d_ctx *c)
     min_rows = std::min(min_rows, r.second - r.first);
   c->persistent = min_rows >= 8;
   c->n_ctas     = c->persistent ? std::min(c->n_items, slots) : c->n_items;
+  if (const char *e = std::getenv("FV2D_MAX_CTAS")) // test / sanitizer knob: few CTAs, many items each
+    if (c->persistent && std::atoi(e) > 0)
+      c->n_ctas = std::min(c->n_ctas, std::atoi(e));
   items.push_back(WorkItem{0, -1, -1, 0}); // end marker
   FV2D_CUDA(cudaMalloc(&c->items_dev, items.size() * sizeof(WorkItem)));
   FV2D_CUDA(cudaMemcpyAsync(c->items_dev, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, c->stream));

@@ -729,8 +729,6 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
       break;
     if constexpr (!PLAIN)
       wait_halo_item(S.item[(ci + 1) & 1]); // the rows of the next item are staged while this one finishes
-    // (thread 0, which does the staging, wrote that entry itself; a thread that still sees the slot's
-    //  previous content waits for nothing it needs)
     const int j0 = item.j0, j1 = item.j1; // rows [j0, j1) are updated
     const int i0    = p.ibeg + item.strip * W; // first interior column of the strip
     const int col   = i0 - 2 + t;              // this thread's column
@@ -1044,10 +1042,12 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
         if (k >= j0)
           mbar_wait(&S.ufull[us], uph);
         {
+          // (only the threads that own a cell of the strip read the box: the two halo threads a side
+          //  would alias the edge threads' elements, which those overwrite with U^{n+1} below)
           const double *ub = &S.uring[us][0][0];
 #pragma unroll
           for (int f = 0; f < 4; ++f)
-            un[f] = ub[f * W + tu];
+            un[f] = (t >= 2 && t < NT - 2) ? ub[f * W + tu] : 0.0;
         }
 
         // y fluxes back in the grid frame: (m, t, n, e) -> (rho, rho u, rho v, E)
@@ -1300,6 +1300,13 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
       if (n_lo + n_hi > 0)
         __threadfence_system();
     }
+    if (t == 0)
+    {
+      // the table entry that landed in item_in is the item after next; it takes the current item's
+      // slot (read by everybody when the item started, and again after the barrier below)
+      cp_async_wait_all();
+      S.item[ci & 1] = S.item_in;
+    }
     __syncthreads();
     if (t == 0)
     {
@@ -1327,11 +1334,8 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
 #else
       stage_u_next(kNU - 1, (uint32_t)us_prev);
 #endif
-      // the next item becomes the current one; the entry that landed in item_in is the one after it
-      cp_async_wait_all();
-      const WorkItem e2 = S.item_in;
-      S.item[ci & 1]    = e2;
-      publish_next(e2);
+      // the next item becomes the current one: publish the one after it to the producer
+      publish_next(S.item[ci & 1]);
     }
   }
 

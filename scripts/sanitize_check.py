@@ -19,7 +19,8 @@ from fv2d_b200 import capi  # noqa: E402
 CASES = [("kh_plm_128x64", {"mesh.Nx": 600, "mesh.Ny": 150}), ("c91_64x32", {"mesh.Nx": 300, "mesh.Ny": 90}),
          ("c91_plm_64x32", {"mesh.Nx": 260, "mesh.Ny": 40}), ("gresho_rk2_32", {"mesh.Nx": 280, "mesh.Ny": 70}),
          ("rt_fslp_32x96", {"mesh.Nx": 270, "mesh.Ny": 60}), ("blast_64", {"mesh.Nx": 300, "mesh.Ny": 64})]
-os.environ["FV2D_CHUNK_ROWS"] = "23"
+os.environ["FV2D_CHUNK_ROWS"] = "11"
+os.environ["FV2D_MAX_CTAS"] = "3"  # few CTAs, several work items each: the cross-item TMA streams are exercised
 for name, ov in CASES:
     dev, run = capi.params_from_ini(load_golden(name).ini_path(), ov)
     Q0 = capi.init_problem(dev, run)

@@ -12,10 +12,12 @@ from fv2d_b200 import capi
 pytestmark = pytest.mark.gpu
 
 
-def _run(dev, run, Q0, nsteps, fused=True, chunk_rows=None):
+def _run(dev, run, Q0, nsteps, fused=True, chunk_rows=None, max_ctas=None):
     old = os.environ.get("FV2D_CHUNK_ROWS")
     if chunk_rows:
         os.environ["FV2D_CHUNK_ROWS"] = str(chunk_rows)
+    if max_ctas:
+        os.environ["FV2D_MAX_CTAS"] = str(max_ctas)
     try:
         with capi.Context(dev, run.time_stepping, run.epsilon_reset_negative) as ctx:
             ctx.upload_Q(Q0)
@@ -36,6 +38,7 @@ def _run(dev, run, Q0, nsteps, fused=True, chunk_rows=None):
                 dts = np.array(dts)
             return ctx.download_Q(), ctx.download_U(), dts, m0, ctx.mass_energy(), ctx.negative_counts()
     finally:
+        os.environ.pop("FV2D_MAX_CTAS", None)
         if chunk_rows:
             if old is None:
                 os.environ.pop("FV2D_CHUNK_ROWS", None)
@@ -150,3 +153,22 @@ def test_degenerate_grid_sizes(name, nx, ny):
     db = b[1][:, dev.jbeg:dev.jend, dev.ibeg:dev.iend]
     scale = float(np.sum(np.abs(db)))
     assert float(np.sum(np.abs(da - db))) <= 1e-12 * scale
+
+
+@pytest.mark.parametrize("name,ov", [("kh_plm_128x64", {"mesh.Nx": 777, "mesh.Ny": 336}),
+                                     ("c91_64x32", {"mesh.Nx": 300, "mesh.Ny": 150}),
+                                     ("gresho_rk2_32", {"mesh.Nx": 260, "mesh.Ny": 128}),
+                                     ("blast_64", {"mesh.Nx": 520, "mesh.Ny": 296})])
+def test_result_does_not_depend_on_how_the_work_items_are_dealt_out(name, ov):
+    """The persistent sweep: however many CTAs share the work table (1, 2, 7 CTAs pulling dozens of
+    items each through the cross-item TMA streams, or one CTA per item), whatever the run height,
+    the result is bitwise the same - every cell's update depends on its stencil only."""
+    dev, run = capi.params_from_ini(load_golden(name).ini_path(), ov)
+    Q0 = capi.init_problem(dev, run)
+    ref = _run(dev, run, Q0, 6)
+    for kw in ({"max_ctas": 1}, {"max_ctas": 2}, {"max_ctas": 7}, {"chunk_rows": 11, "max_ctas": 3}, {"chunk_rows": 3},
+               {"chunk_rows": 40, "max_ctas": 5}):
+        got = _run(dev, run, Q0, 6, **kw)
+        assert np.array_equal(got[1], ref[1]), kw   # U, ghosts included
+        assert np.array_equal(got[0], ref[0]), kw   # Q
+        assert np.array_equal(got[2], ref[2]), kw   # dt sequence
