@@ -18,6 +18,10 @@ $(OBJDIR)/fv2d_ops.o: $(CSRC)/fv2d_ops.cu $(HOSTHDR)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) --fmad=false -c $< -o $@
 
+$(OBJDIR)/fv2d_stream.o: $(CSRC)/fv2d_stream.cu $(HOSTHDR)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) --fmad=false -c $< -o $@
+
 # the fused sweep: dispatcher + small kernels, and one translation unit per Riemann solver
 # (0 = HLL, 1 = HLLC, 2 = FSLP) holding that solver's 36 kernel instantiations (parallel under -j)
 $(OBJDIR)/fv2d_sweep.o: $(CSRC)/fv2d_sweep.cu $(HOSTHDR)
@@ -33,7 +37,7 @@ $(OBJDIR)/fv2d_capi.o: $(CSRC)/fv2d_capi.cu $(HOSTHDR)
 	$(NVCC) $(NVFLAGS) -Xcompiler -fopenmp -c $< -o $@
 
 SWEEPOBJ := $(OBJDIR)/fv2d_sweep.o $(OBJDIR)/fv2d_sweep_s0.o $(OBJDIR)/fv2d_sweep_s1.o $(OBJDIR)/fv2d_sweep_s2.o
-$(LIB): $(OBJDIR)/fv2d_ops.o $(SWEEPOBJ) $(OBJDIR)/fv2d_capi.o
+$(LIB): $(OBJDIR)/fv2d_ops.o $(OBJDIR)/fv2d_stream.o $(SWEEPOBJ) $(OBJDIR)/fv2d_capi.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static -Xcompiler -fopenmp
 
 fv2d_b200/fv2d_b200_main: fv2d_b200/host/main.cpp $(HOSTHDR) $(LIB)

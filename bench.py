@@ -205,14 +205,17 @@ class Job:
         self.ctx.compute_dt()
         self.ctx.sync()
 
-    def timed(self, steps):
+    def timed(self, steps, bracket_launches=False):
         """`steps` fused steps between barrier + synchronize, CUDA events on the context's stream,
-        maximum over the ranks.  Returns (ms, sweep_ms, sweep_launches, all_launches) of this region."""
+        maximum over the ranks.  Returns (ms, sweep_ms, sweep_launches, all_launches) of this region.
+        sweep_ms: by default the region itself (the sweep is the only kernel of a step; consecutive
+        launches overlap prologue and tail, so a launch's share of the region is region / launches);
+        with bracket_launches every launch gets its own event pair (and runs on its own)."""
         import torch
 
         env, ctx = self.env, self.ctx
         ctx.sync_wait(reset=True)
-        ctx.profile_enable(True)
+        ctx.profile_enable(1 if bracket_launches else 2)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         env.barrier()
         with torch.cuda.stream(env.stream):
@@ -220,9 +223,12 @@ class Job:
             ctx.run_steps(steps)
             e1.record(env.stream)
         env.barrier()
-        ms = env.max_over_ranks(e0.elapsed_time(e1))
+        ms_local = e0.elapsed_time(e1)
+        ms = env.max_over_ranks(ms_local)
         sweep_ms, sweep_launches, total_launches = ctx.profile_read()
-        ctx.profile_enable(False)
+        if not bracket_launches:
+            sweep_ms = ms_local
+        ctx.profile_enable(0)
         # per-step wait of this rank's first CTA for the other ranks' CFL mails (the decomposition's
         # synchronisation cost; 0 on one GPU), maximum over the ranks
         self.cfl_wait_us = env.max_over_ranks(ctx.sync_wait()[1] / max(sweep_launches, 1))
@@ -342,6 +348,11 @@ def native_arm(args):
         s_per_launch, s_achieved, s_frac = job.roofline(s_sweep_ms, s_launches, peak)
         sustained = {"steps": n_sus, "ms_per_step": s_ms / n_sus, "value": Nx * Ny * n_sus / (s_ms * 1e-3) / 1e6,
                      "unit": "Mcell-updates/s", "frac": s_frac, "ms_per_launch": s_per_launch * 1e3, "clocks": s_clocks}
+    # ---- the same kernel with every launch bracketed by its own event pair (launches then run one
+    #      after the other, no overlap of a launch's prologue with the previous one's tail)
+    b_ms, b_sweep_ms, b_launches, _ = job.timed(min(args.steps, 20), bracket_launches=True)
+    bracketed = {"steps": min(args.steps, 20), "ms_per_launch": b_sweep_ms / max(b_launches, 1),
+                 "ms_per_step": b_ms / min(args.steps, 20), "share_of_step": b_sweep_ms / b_ms if b_ms > 0 else None}
     neg = ctx.negative_counts()
 
     traffic = None
@@ -378,20 +389,52 @@ def native_arm(args):
         hin = torch.from_numpy(job.Qloc).pin_memory()
         hout = torch.empty_like(hin).pin_memory()
         a_in, a_out = hin.numpy(), hout.numpy()
-        dts = np.zeros(1)
-        ctx.advance_host(a_in, a_out, 1, dts)  # warm-up
-        a_in, a_out = a_out, a_in
-        env.barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            ctx.advance_host(a_in, a_out, 1, dts)
-            a_in, a_out = a_out, a_in
-        env.barrier()
-        secs = env.max_over_ranks(time.perf_counter() - t0)
         nbytes = int(job.Qloc.nbytes) * world
-        e2e = {"value": Nx * Ny * args.e2e_steps / secs / 1e6, "unit": "Mcell-updates/s",
-               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 8 * world, "steps": args.e2e_steps,
-               "api": "fv2d_advance_host(ctx, hostQ_in, hostQ_out, 1, &dt)" + (" on every rank's y-slab" if world > 1 else "")}
+
+        def serial(n):
+            """fv2d_advance_host: upload, computeDt, step, download - one transfer after the other"""
+            nonlocal a_in, a_out
+            dts = np.zeros(1)
+            env.barrier()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                ctx.advance_host(a_in, a_out, 1, dts)
+                a_in, a_out = a_out, a_in
+            env.barrier()
+            return env.max_over_ranks(time.perf_counter() - t0)
+
+        serial(1)  # warm-up
+        if world == 1:
+            # the streamed call: the state moves in row blocks, upload | sweep | download overlapped; the
+            # dt each call announces for its output is the next call's hint and is verified on the way
+            _, hint, _ = ctx.advance_host_stream(a_in, a_out, 0.0)  # first call of a chain: no hint
+            a_in, a_out = a_out, a_in
+            _, hint, _ = ctx.advance_host_stream(a_in, a_out, hint)  # warm-up of the streamed path
+            a_in, a_out = a_out, a_in
+            env.barrier()
+            n_streamed = 0
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                _, hint, st = ctx.advance_host_stream(a_in, a_out, hint)
+                n_streamed += int(st)
+                a_in, a_out = a_out, a_in
+            env.barrier()
+            secs = time.perf_counter() - t0
+            secs_serial = serial(min(args.e2e_steps, 3))
+            row_bytes = 4 * 8 * (Nx + 2 * job.dev.Ng)
+            up_rows = Ny + (job.dev.Ng if job.dev.boundary_y == capi.BC_PERIODIC else 0)
+            e2e = {"value": Nx * Ny * args.e2e_steps / secs / 1e6, "unit": "Mcell-updates/s",
+                   "h2d_bytes_per_step": row_bytes * up_rows, "d2h_bytes_per_step": nbytes + 8 * 64,
+                   "steps": args.e2e_steps, "steps_streamed": n_streamed, "ms_per_step": 1e3 * secs / args.e2e_steps,
+                   "api": "fv2d_advance_host_stream(ctx, hostQ_in, hostQ_out, dt_hint = dt_next of the previous call, "
+                          "&dt_used, &dt_next, &streamed): pinned host arrays, one step per call, hint verified per call",
+                   "serial": {"value": Nx * Ny * min(args.e2e_steps, 3) / secs_serial / 1e6, "unit": "Mcell-updates/s",
+                              "api": "fv2d_advance_host(ctx, hostQ_in, hostQ_out, 1, &dt): upload, step, download in turn"}}
+        else:
+            secs = serial(args.e2e_steps)
+            e2e = {"value": Nx * Ny * args.e2e_steps / secs / 1e6, "unit": "Mcell-updates/s",
+                   "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 8 * world, "steps": args.e2e_steps,
+                   "api": "fv2d_advance_host(ctx, hostQ_in, hostQ_out, 1, &dt) on every rank's y-slab"}
         del hin, hout, a_in, a_out
     host_init_s, slab_gb = job.host_init_s, job.Qloc.nbytes * world / 1e9
     job.close()
@@ -444,7 +487,9 @@ def native_arm(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": frac,
                          "traffic": traffic, "kernel": "k_sweep (fused RK stage, persistent)", "peak_source": peak_src,
                          "bytes_per_cell_update": BYTES_PER_CELL_UPDATE, "ms_per_launch": per_launch_s * 1e3,
-                         "share_of_step": sweep_ms / ms if ms > 0 else None, "fp64": fp64,
+                         "launch_duration_is": "timed region / launches in it (one kernel per step, launched back to back "
+                                               "with programmatic stream serialization)",
+                         "event_bracketed_launches": bracketed, "share_of_step": bracketed["share_of_step"], "fp64": fp64,
                          "cfl_mail_wait_us_per_step": cfl_wait_main},
             "sustained": sustained, "state_hash": {"after_steps": HASH_STEPS, "u64": f"0x{state_hash:016x}"},
             "strong_16384": strong_16384, "weak": weak,
@@ -466,7 +511,7 @@ def main():
     ap.add_argument("--workload", default="kelvin_helmholtz_8192_plm_hllc", choices=sorted(WORKLOADS))
     ap.add_argument("--nx", type=int, default=0, help="override Nx (development only)")
     ap.add_argument("--ny", type=int, default=0, help="override Ny (development only)")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--reps", type=int, default=3, help="repetitions of the timed region; the median is reported")
     ap.add_argument("--sustained-steps", type=int, default=200, help="length of the sustained-regime region (0: skip)")
     ap.add_argument("--side-steps", type=int, default=20, help="timed steps of the strong_16384 / weak blocks")

@@ -184,6 +184,7 @@ def lib() -> C.CDLL:
         "fv2d_get_negative_counts": [_ctxp, C.POINTER(C.c_uint64), C.c_int],
         "fv2d_integrate_mass_energy": [_ctxp, _dp, _dp],
         "fv2d_advance_host": [_ctxp, _dp, _dp, C.c_int64, _dp],
+        "fv2d_advance_host_stream": [_ctxp, _dp, _dp, C.c_double, _dp, _dp, C.POINTER(C.c_int)],
         "fv2d_profile_enable": [_ctxp, C.c_int],
         "fv2d_profile_read": [_ctxp, _dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
         "fv2d_halo_export": [_ctxp, C.c_void_p],
@@ -479,6 +480,14 @@ class Context:
 
     def advance_host(self, Q_in: np.ndarray, Q_out: np.ndarray, nsteps: int, dts: np.ndarray | None = None):
         _check(lib().fv2d_advance_host(self._h, _ptr(Q_in), _ptr(Q_out), nsteps, _ptr(dts) if dts is not None else None))
+
+    def advance_host_stream(self, Q_in: np.ndarray, Q_out: np.ndarray, dt_hint: float = 0.0):
+        """One step on a host-resident state with overlapped transfers (fv2d_advance_host_stream).
+        Returns (dt_used, dt_next, streamed): pass dt_next as the next call's dt_hint."""
+        used, nxt, st = C.c_double(0.0), C.c_double(0.0), C.c_int(0)
+        _check(lib().fv2d_advance_host_stream(self._h, _ptr(Q_in), _ptr(Q_out), float(dt_hint), C.byref(used), C.byref(nxt),
+                                              C.byref(st)))
+        return used.value, nxt.value, bool(st.value)
 
 
 def exported_symbols_in_header() -> list[str]:

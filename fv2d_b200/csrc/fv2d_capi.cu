@@ -2,6 +2,7 @@
 // transfers, the operator-level entry points and the fused step driver.
 #include <cmath>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -833,6 +834,20 @@ void fv2d_ctx_destroy(fv2d_ctx *c)
   cudaFree(c->items_dev);
   cudaFree(c->tmaps_dev);
   cudaFree(c->rowsum);
+  cudaFree(c->sitems_dev);
+  cudaFree(c->dense_in);
+  cudaFree(c->dense_out);
+  if (c->s_ev)
+  {
+    for (int k = 0; k < 2 * c->n_sblocks + 2; ++k)
+      cudaEventDestroy(c->s_ev[k]);
+    delete[] c->s_ev;
+  }
+  delete[] c->sblocks;
+  if (c->s_up)
+    cudaStreamDestroy(c->s_up);
+  if (c->s_dn)
+    cudaStreamDestroy(c->s_dn);
   cudaFree(c->sc);
   if (c->prof_ev)
   {
@@ -1338,7 +1353,7 @@ int fv2d_profile_enable(fv2d_ctx *c, int on)
     for (int k = 0; k < 2 * kProfMax; ++k)
       FV2D_CUDA(cudaEventCreate(&c->prof_ev[k]));
   }
-  c->profile        = on != 0;
+  c->profile        = on == 1; // on == 2: count the launches, record no events
   c->prof_n         = 0;
   c->n_launch_sweep = 0;
   c->n_launch_total = 0;
@@ -1360,7 +1375,7 @@ int fv2d_profile_read(fv2d_ctx *c, double *sweep_ms, int64_t *sweep_launches, in
   if (sweep_ms)
     *sweep_ms = ms;
   if (sweep_launches)
-    *sweep_launches = c->prof_n;
+    *sweep_launches = c->profile ? c->prof_n : c->n_launch_sweep;
   if (total_launches)
     *total_launches = c->n_launch_total;
   return FV2D_OK;
@@ -1401,6 +1416,280 @@ int fv2d_advance_host(fv2d_ctx *c, const double *hostQ_in, double *hostQ_out, in
     return fv2d_get_dt_history(c, dts, nsteps, &got);
   }
   return sync_ctx(c);
+}
+
+// ------------------------------------------------------------------ streamed host path
+
+// array rows [r0, r1) of the four field planes between the host array [f][Nty][Ntx] and its device
+// copy in the same layout: one flat copy per plane
+static int copy_rows(fv2d_ctx *c, double *dense, double *host, int r0, int r1, bool to_device, cudaStream_t s)
+{
+  if (r1 <= r0)
+    return FV2D_OK;
+  const size_t Ntx = (size_t)c->kp.p.Ntx, rows = (size_t)c->kp.L.rows;
+  const size_t bytes = (size_t)(r1 - r0) * Ntx * sizeof(double);
+  for (int f = 0; f < 4; ++f)
+  {
+    const size_t o = ((size_t)f * rows + (size_t)r0) * Ntx;
+    if (to_device)
+      FV2D_CUDA(cudaMemcpyAsync(dense + o, host + o, bytes, cudaMemcpyHostToDevice, s));
+    else
+      FV2D_CUDA(cudaMemcpyAsync(host + o, dense + o, bytes, cudaMemcpyDeviceToHost, s));
+  }
+  return FV2D_OK;
+}
+
+// Row blocks of the streamed path and the work table of each block's partial sweep.  Block b brings
+// up domain rows [up0, up1); the rows whose 2-row stencil is complete by then, [sw0, sw1), are swept.
+static int ensure_stream_blocks(fv2d_ctx *c)
+{
+  if (c->sblocks)
+    return FV2D_OK;
+  const fv2d_device_params &p = c->kp.p;
+  int B = 256;
+  if (const char *e = std::getenv("FV2D_STREAM_ROWS"))
+    if (std::atoi(e) >= 16)
+      B = std::atoi(e);
+  const int nb = std::max(1, p.Ny / B);
+  const int W = sweep_strip_width(), nstrips = (p.Nx + W - 1) / W, slots = 2 * c->num_sms;
+  std::vector<WorkItem> items;
+  fv2d_ctx::StreamBlock *blk = new fv2d_ctx::StreamBlock[nb];
+  bool ok = true;
+  for (int b = 0; b < nb; ++b)
+  {
+    fv2d_ctx::StreamBlock &k = blk[b];
+    k.up0 = p.jbeg + b * B;
+    k.up1 = (b == nb - 1) ? p.jend : p.jbeg + (b + 1) * B;
+    k.sw0 = (b == 0) ? p.jbeg : blk[b - 1].sw1;
+    k.sw1 = (b == nb - 1) ? p.jend : k.up1 - 2;
+    const std::vector<std::pair<int, int>> runs = schedule_runs(k.sw1 - k.sw0, nstrips, slots, false, false);
+    k.item_off = (int)items.size();
+    int min_rows = k.sw1 - k.sw0;
+    for (const auto &r : runs)
+    {
+      min_rows = std::min(min_rows, r.second - r.first);
+      for (int s = 0; s < nstrips; ++s)
+        items.push_back(WorkItem{s, k.sw0 + r.first, k.sw0 + r.second, 0});
+    }
+    k.n_items    = (int)items.size() - k.item_off;
+    k.persistent = min_rows >= 8;
+    k.n_ctas     = k.persistent ? std::min(k.n_items, slots) : k.n_items;
+    ok           = ok && k.sw1 > k.sw0;
+    items.push_back(WorkItem{0, -1, -1, 0}); // end marker of this block's table
+  }
+  if (!ok)
+  {
+    delete[] blk;
+    return arg_fail("streamed path: grid too small for the row blocks");
+  }
+  FV2D_CUDA(cudaMalloc(&c->sitems_dev, items.size() * sizeof(WorkItem)));
+  FV2D_CUDA(cudaMemcpyAsync(c->sitems_dev, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, c->stream));
+  FV2D_CUDA(cudaStreamSynchronize(c->stream));
+  const size_t dense_bytes = (size_t)4 * p.Nty * p.Ntx * sizeof(double);
+  FV2D_CUDA(cudaMalloc(&c->dense_in, dense_bytes));
+  FV2D_CUDA(cudaMalloc(&c->dense_out, dense_bytes));
+  FV2D_CUDA(cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking));
+  FV2D_CUDA(cudaStreamCreateWithFlags(&c->s_dn, cudaStreamNonBlocking));
+  c->s_ev = new cudaEvent_t[2 * nb + 2];
+  for (int k = 0; k < 2 * nb + 2; ++k)
+    FV2D_CUDA(cudaEventCreateWithFlags(&c->s_ev[k], cudaEventDisableTiming));
+  c->sblocks   = blk;
+  c->n_sblocks = nb;
+  return FV2D_OK;
+}
+
+static double next_dt_of(const fv2d_device_params &p, double hyp)
+{
+  double tc = p.epsilon, visc = p.epsilon;
+  if (p.thermal_conductivity_active)
+    tc = std::fmax(2.0 * p.kappa / (p.dx * p.dx), 2.0 * p.kappa / (p.dy * p.dy));
+  if (p.viscosity_active)
+    visc = std::fmax(2.0 * p.mu / (p.dx * p.dx), 2.0 * p.mu / (p.dy * p.dy));
+  double m = hyp;
+  if (m < tc)
+    m = tc;
+  if (m < visc)
+    m = visc;
+  return p.CFL / m;
+}
+
+int fv2d_advance_host_stream(fv2d_ctx *c, const double *hostQ_in, double *hostQ_out, double dt_hint, double *dt_used,
+                             double *dt_next, int *streamed)
+{
+  FV2D_ENTER(c);
+  if (!hostQ_in || !hostQ_out)
+    return arg_fail("null host array");
+  if (!c->tmap_ok)
+    return arg_fail("TMA descriptors unavailable");
+  if (c->nranks > 1 && !c->connected)
+    return arg_fail("multi-GPU context: call fv2d_halo_connect before stepping");
+  int rc;
+  const fv2d_device_params &p = c->kp.p;
+  static const unsigned long long neg_max = FV2D_ENC_NEG_MAX;
+  double *hin = const_cast<double *>(hostQ_in);
+  if (streamed)
+    *streamed = 0;
+  c->ghosts_valid = c->dt_valid = false;
+  FV2D_CUDA(cudaMemcpyAsync(&c->sc->inv_acc[0][0], &neg_max, sizeof neg_max, cudaMemcpyHostToDevice, c->stream));
+
+  // Speculation needs: a dt to speculate with, a single slab (the check of the hint is a local
+  // decision), one sweep per step, and ghost cells the sweep can write itself.
+  const bool speculate = dt_hint > 0.0 && c->nranks == 1 && c->time_stepping != FV2D_TS_RK2 && c->fold_ok &&
+                         !std::getenv("FV2D_STREAM_OFF");
+  bool need_plain_step = true;
+  if (speculate)
+  {
+    if ((rc = ensure_stream_blocks(c)))
+      return rc;
+    const int cur = c->cur, nxt = cur ^ 1, nb = c->n_sblocks;
+    cudaEvent_t *ev = c->s_ev;
+    // the copy streams start after whatever the context's stream still has in flight
+    FV2D_CUDA(cudaMemcpyAsync(c->sc->neg_save, c->sc->neg, sizeof(c->sc->neg), cudaMemcpyDeviceToDevice, c->stream));
+    FV2D_CUDA(cudaEventRecord(ev[2 * nb], c->stream));
+    FV2D_CUDA(cudaStreamWaitEvent(c->s_up, ev[2 * nb], 0));
+    FV2D_CUDA(cudaStreamWaitEvent(c->s_dn, ev[2 * nb], 0));
+    // development: where the call's time goes (FV2D_STREAM_TRACE=1 prints a line per call)
+    static const bool trace = std::getenv("FV2D_STREAM_TRACE") != nullptr;
+    static cudaEvent_t tev[4];
+    static bool tev_ok = false;
+    const auto host_t0 = std::chrono::steady_clock::now();
+    if (trace)
+    {
+      if (!tev_ok)
+        for (auto &e : tev)
+          cudaEventCreate(&e);
+      tev_ok = true;
+      cudaEventRecord(tev[0], c->s_up);
+    }
+    // a periodic y boundary mirrors the LAST domain rows into the low ghost rows: bring them up first
+    if (p.boundary_y == FV2D_BC_PERIODIC)
+    {
+      if ((rc = copy_rows(c, c->dense_in, hin, p.jend - p.Ng, p.jend, true, c->s_up)))
+        return rc;
+      FV2D_CUDA(cudaEventRecord(ev[2 * nb + 1], c->s_up));
+      FV2D_CUDA(cudaStreamWaitEvent(c->stream, ev[2 * nb + 1], 0));
+      launch_prep_rows(c->kp, c->dense_in, c->Q[cur], c->U, p.jend - p.Ng, p.jend, &c->sc->inv_acc[0][0], c->stream);
+      c->n_launch_total++;
+    }
+
+    SweepArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.kp            = c->kp;
+    a.use_device_dt = 0;
+    a.dt_host       = dt_hint;
+    a.fold_ghosts   = 1;
+    a.lo_rank = a.hi_rank = 0;
+    a.mail_gen      = c->mail_gen;
+    a.Uin = c->U, a.Uout = c->U, a.U0 = nullptr, a.Qout = c->Q[nxt], a.final_stage = 1, a.partial = 1;
+    a.tm_store_u = c->tmaps_dev;
+    NvtxRange step_range("streamed step: upload | ghost fill + primToCons + fused sweep | download, by row blocks");
+    for (int b = 0; b < nb; ++b)
+    {
+      const fv2d_ctx::StreamBlock &k = c->sblocks[b];
+      if ((rc = copy_rows(c, c->dense_in, hin, k.up0, k.up1, true, c->s_up)))
+        return rc;
+      FV2D_CUDA(cudaEventRecord(ev[2 * b], c->s_up));
+      FV2D_CUDA(cudaStreamWaitEvent(c->stream, ev[2 * b], 0));
+      // the block's rows into the padded planes, U and the CFL maximum on the way; then the ghost cells:
+      // the x-ghost columns of the block's rows, the low y-ghost rows with the first block, the high
+      // ones with the last (their source rows are resident by then)
+      launch_prep_rows(c->kp, c->dense_in, c->Q[cur], c->U, k.up0, k.up1, &c->sc->inv_acc[0][0], c->stream);
+      const int g0 = (b == 0) ? 0 : k.up0, g1 = (b == nb - 1) ? p.Nty : k.up1;
+      launch_fill_ghosts_rows(c->kp, c->Q[cur], c->U, g0, g1, c->stream);
+      a.items      = c->sitems_dev + k.item_off;
+      a.n_items    = k.n_items;
+      a.n_ctas     = k.n_ctas;
+      a.persistent = k.persistent;
+      cudaError_t e = launch_sweep(c->tmapQ[cur], c->tmapU, a, c->stream);
+      if (e != cudaSuccess)
+        return cuda_fail(e, "partial sweep", __FILE__, __LINE__);
+      // the swept rows (and, with the last block, the y-ghost rows the first and last sweeps wrote) go
+      // back in the host's layout
+      const int d0 = k.sw0, d1 = (b == nb - 1) ? p.Nty : k.sw1;
+      launch_pack_rows(c->kp, c->Q[nxt], c->dense_out, d0, d1, c->stream);
+      if (b == nb - 1)
+        launch_pack_rows(c->kp, c->Q[nxt], c->dense_out, 0, p.jbeg, c->stream);
+      c->n_launch_sweep++;
+      c->n_launch_total += 4 + (b == nb - 1);
+      FV2D_CUDA(cudaEventRecord(ev[2 * b + 1], c->stream));
+      FV2D_CUDA(cudaStreamWaitEvent(c->s_dn, ev[2 * b + 1], 0));
+      if ((rc = copy_rows(c, c->dense_out, hostQ_out, d0, d1, false, c->s_dn)))
+        return rc;
+    }
+    if ((rc = copy_rows(c, c->dense_out, hostQ_out, 0, p.jbeg, false, c->s_dn)))
+      return rc;
+    launch_stream_commit(c->kp, dt_hint, c->mail_gen + 1, c->stream);
+    c->n_launch_total++;
+    FV2D_CUDA(cudaGetLastError());
+    const auto host_t1 = std::chrono::steady_clock::now();
+    if (trace)
+      cudaEventRecord(tev[1], c->s_up), cudaEventRecord(tev[2], c->stream), cudaEventRecord(tev[3], c->s_dn);
+    FV2D_CUDA(cudaStreamSynchronize(c->s_dn));
+    if ((rc = read_scalars(c)))
+      return rc;
+    if (trace)
+    {
+      float up = 0, comp = 0, dn = 0;
+      cudaEventElapsedTime(&up, tev[0], tev[1]), cudaEventElapsedTime(&comp, tev[0], tev[2]), cudaEventElapsedTime(&dn, tev[0], tev[3]);
+      fprintf(stderr, "fv2d stream trace: enqueue %.2f ms (host), uploads done at %.2f ms, kernels at %.2f, downloads at %.2f, call %.2f ms (host)\n",
+              std::chrono::duration<double, std::milli>(host_t1 - host_t0).count(), up, comp, dn,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count());
+    }
+    if (c->sc_host->stream_ok)
+    {
+      c->cur = nxt;
+      c->halo_gen++;
+      c->mail_gen++;
+      c->ghosts_valid = true;
+      c->dt_valid     = true;
+      need_plain_step = false;
+      if (streamed)
+        *streamed = 1;
+      if (dt_used)
+        *dt_used = c->sc_host->dt;
+      if (dt_next)
+        *dt_next = c->sc_host->dt_next;
+    }
+    // else: dt_hint was not the state's own time step.  Q[cur] still holds the uploaded state (with
+    // its ghosts), inv_acc[0] its CFL maximum; U was overwritten by the speculative sweeps.
+  }
+  else
+  {
+    if ((rc = copy_h2d(c, c->Q[c->cur], hostQ_in)))
+      return rc;
+    // (a y-slab's ghost rows on a neighbour side are taken from the host array, like fv2d_upload_Q)
+  }
+  if (need_plain_step)
+  {
+    // dt from the state's CFL maximum in the sweep's arithmetic (so that a call with and a call
+    // without a hint give the same bits), then one ordinary fused step and the whole state back
+    launch_prep_rows(c->kp, nullptr, c->Q[c->cur], c->U, 0, p.Nty, &c->sc->inv_acc[0][0], c->stream);
+    c->mail_gen++;
+    launch_finalize_dt(c->kp, &c->sc->inv_acc[0][0], c->mail_gen, c->stream);
+    c->n_launch_total += 2;
+    c->dt_valid = true;
+    if ((rc = fused_step(c, true, 0.0)))
+      return rc;
+    if (c->nranks > 1)
+    {
+      launch_fill_ghosts(c->kp, c->Q[c->cur], c->halo_gen * pushes_per_sweep(c), c->stream);
+      c->n_launch_total++;
+    }
+    if ((rc = copy_d2h(c, hostQ_out, c->Q[c->cur])))
+      return rc;
+    if ((rc = read_scalars(c)))
+      return rc;
+    if (dt_used)
+      *dt_used = c->sc_host->dt;
+    if (dt_next)
+    {
+      double hyp = 0.0;
+      if ((rc = current_hyp(c, &hyp)))
+        return rc;
+      *dt_next = next_dt_of(p, hyp);
+    }
+  }
+  return FV2D_OK;
 }
 
 // ------------------------------------------------------------------ multi-GPU halo exchange

@@ -70,7 +70,9 @@ struct DevScalars
   unsigned int cta_done;               // CTAs of the running sweep that have finished (local)
   unsigned int fault;                  // set if a wait on a peer timed out
   unsigned int work_next;              // work items handed out beyond the static first one per CTA (local)
-  unsigned int pad0_;
+  unsigned int stream_ok;              // streamed host step: 1 = the caller's dt was the state's own, step committed
+  double dt_next;                      // ... and the time step of the state it produced
+  unsigned long long neg_save[4];      // ... `neg` as it was when the step began (restored if not committed)
   double dt_hist[FV2D_DT_HISTORY];  // ring of dts used
 };
 
@@ -251,6 +253,20 @@ struct fv2d_ctx
   cudaEvent_t *prof_ev; // 2 * kProfMax events
   int prof_n;           // pairs recorded
   long long n_launch_sweep, n_launch_total;
+
+  // streamed host path (fv2d_advance_host_stream): row blocks, their work tables, copy streams
+  struct StreamBlock
+  {
+    int up0, up1;     // array rows uploaded with the block
+    int sw0, sw1;     // domain rows swept once the block is resident (array row indices)
+    int item_off, n_items, n_ctas, persistent;
+  };
+  StreamBlock *sblocks;
+  int n_sblocks;
+  fv2d::WorkItem *sitems_dev;
+  cudaStream_t s_up, s_dn;
+  double *dense_in, *dense_out; // device copies of the host arrays in the host's layout (flat PCIe copies)
+  cudaEvent_t *s_ev; // 2 per block (uploaded, swept) + 2
 
   // multi-GPU peers (slab below / above): the neighbours' Q[0], Q[1] mapped into this device
   double *peerQ_lo[2], *peerQ_hi[2];

@@ -24,6 +24,24 @@ void launch_mass_energy(const KParams &kp, const double *U, double *rowsum, cuda
 void launch_state_hash(const KParams &kp, const double *U, unsigned long long *out, cudaStream_t s);
 void launch_fp64_peak(int blocks, int iters, double *out, cudaStream_t s);
 
+// ---- streamed host path (fv2d_stream.cu): what a state arriving from the host row block by row block needs
+// Ghost cells inside array rows [ra, rb) of a single slab's Q (x-ghost columns of domain rows, whole
+// y-ghost rows), composed x/y boundary passes as in k_fill_boundaries, and U = primToCons of them; the
+// source rows must be resident.
+void launch_fill_ghosts_rows(const KParams &kp, double *Q, double *U, int ra, int rb, cudaStream_t s);
+// Array rows [ra, rb), all columns: [Q = the rows of `dense`, the device copy of the host array in the
+// host's own layout, if dense != nullptr;] U = primToCons(Q); the hyperbolic CFL maximum of the DOMAIN
+// cells among them - in the sweep's arithmetic, so that it equals bit for bit what the sweep that
+// produced the state left behind - accumulated into *acc (order-preserving encoding, atomicMax).
+void launch_prep_rows(const KParams &kp, const double *dense, double *Q, double *U, int ra, int rb, unsigned long long *acc,
+                      cudaStream_t s);
+// Array rows [ra, rb) of Q, all columns, into the dense (host-layout) staging array.
+void launch_pack_rows(const KParams &kp, const double *Q, double *dense, int ra, int rb, cudaStream_t s);
+// Ends a streamed step taken with the caller's dt (`hint`): if the input state's own CFL time step
+// (from inv_acc[0]) equals `hint` the step is committed (clock, dt history, CFL mail `mail_gen` of the
+// new state from inv_acc[1], sc->stream_ok = 1), else the speculative bookkeeping is undone (stream_ok = 0).
+void launch_stream_commit(const KParams &kp, double hint, unsigned long long mail_gen, cudaStream_t s);
+
 // ---- fused hot path (fv2d_sweep.cu)
 
 // Stand-alone ghost fill of Q (composed x/y passes; waits for `halo_expected` pushed rows on a
@@ -42,6 +60,8 @@ struct SweepArgs
   const double *U0; // RK2 stage 2: the state at the start of the step; else nullptr
   double *Qout;
   int final_stage;   // 1: checkNegatives + dt reduction of the new state + clock advance
+  int partial;       // 1: the launch covers only part of the slab's rows (streamed host path): its CFL maximum stays
+                     // in the accumulator, no mail, no clock advance - fv2d_stream.cu commits the step
   int use_device_dt; // 1: dt = CFL / max(inverse time-steps mailed by generation `mail_gen`); 0: dt = dt_host
   double dt_host;
   int fold_ghosts;   // 1: the epilogue also writes the ghost cells of Qout (boundary conditions)

@@ -34,6 +34,7 @@
 // conditions, BoundaryConditions.h:82-147, or the neighbour slab's halo rows) are written by the
 // epilogue of the rows they mirror, and the clock (t += dt) is advanced by the sweep's last CTA.
 #include "fv2d_kernels.h"
+#include "fv2d_fastmath.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -118,12 +119,6 @@ __device__ __forceinline__ int bc_src(int bc, int k, int beg, int end, int N)
 }
 
 // Development knobs for the A/B variants built by scripts/build_variant.sh (defaults = shipped).
-#ifndef FV2D_FAST_RCP
-#define FV2D_FAST_RCP 1
-#endif
-#ifndef FV2D_FAST_CS
-#define FV2D_FAST_CS 1
-#endif
 #ifndef FV2D_PS_SHORT
 #define FV2D_PS_SHORT 1
 #endif
@@ -133,50 +128,6 @@ __device__ __forceinline__ int bc_src(int bc, int k, int beg, int end, int N)
 #ifndef FV2D_HLLC_UNIFORM
 #define FV2D_HLLC_UNIFORM 0 // 1: select-free HLLC tail when a whole warp takes the same branch (measured slower)
 #endif
-
-// 1/a: MUFU.RCP64H seed (relative error e0 <= ~2^-18) + ONE third-order step
-//   y1 = y0 (1 + e + e^2),  e = 1 - a y0   ->  relative error e0^3 < 2^-54, i.e. ~1 ulp with
-// the rounding of the last fma; three dependent DFMAs, no IEEE slow path.  (div.rn.f64 itself
-// starts with exactly this step and then spends five more instructions on correct rounding.)
-__device__ __forceinline__ double frcp(double a)
-{
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-#if FV2D_FAST_RCP
-  const double e = fma(-a, y, 1.0);
-  const double t = fma(e, e, e);
-  return fma(y, t, y);
-#else
-  double e = fma(-a, y, 1.0);
-  y        = fma(y, e, y);
-  e        = fma(-a, y, 1.0);
-  y        = fma(y, e, y);
-  return y;
-#endif
-}
-// sound speed sqrt(gp / rho) with gp = gamma0 * P:  c = gp * rsqrt(gp * rho).
-// MUFU.RSQ64H seed r + ONE third-order step  1/sqrt(y) = r (1 + e/2 + 3 e^2 / 8),
-// e = 1 - y r^2  (|e| <= ~2^-17 -> truncation 5 e^3 / 16 < 2^-52): 7 fp64 instructions.
-__device__ __forceinline__ double csound(double gp, double rho)
-{
-  const double y = gp * rho;
-  double r;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
-#if FV2D_FAST_CS
-  const double e = fma(-y, r * r, 1.0);
-  const double t = fma(0.375, e, 0.5) * e;
-  return gp * fma(r, t, r);
-#else
-  double g = y * r;   // ~ sqrt(y)
-  double h = 0.5 * r; // ~ 1 / (2 sqrt(y))
-  double e = fma(-g, h, 0.5);
-  g        = fma(g, e, g);
-  h        = fma(h, e, h);
-  e        = fma(-g, h, 0.5);
-  h        = fma(h, e, h);
-  return (gp + gp) * h;
-#endif
-}
 
 // max / min as one DSETP + two FSEL.  fmax()/fmin() lower to ~8 instructions each on sm_100a
 // (NaN-propagation fix-ups); the operands here are never NaN unless the state already is, and
@@ -614,11 +565,9 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
     S.nx_j1    = e.j1;
   };
 
-  if constexpr (!PLAIN)
-    wait_halo_item(a.items[blockIdx.x]); // the CTA's first item (all threads: see wait_halo_item)
-
-  // ---- kernel prologue (thread 0): barriers, the first two work items, the initial fill of both
-  // rings, and this step's dt
+  // ---- kernel prologue, part 1 (thread 0): everything that does not depend on the previous launch -
+  // barriers and the CTA's first work item (the table is static).  The sweep is launched with
+  // programmatic stream serialization: this part runs while the previous sweep's last CTAs finish.
   if (t == 0)
   {
 #pragma unroll
@@ -629,16 +578,21 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
       mbar_init(&S.ufull[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    // the first item is static (CTA b starts on item b), the second comes from the counter; with
-    // a.persistent == 0 (degenerate grids: items of fewer than 8 rows) every CTA has just its one item
-    const WorkItem e0 = a.items[blockIdx.x];
-    unsigned i1       = (unsigned)a.n_items;
-    if (a.persistent)
-      i1 = min(gridDim.x + atomicAdd(&sc->work_next, 1u), (unsigned)a.n_items);
+    S.item[0] = a.items[blockIdx.x]; // the first item is static: CTA b starts on item b
     S.item_in = WorkItem{0, -1, -1, 0};
-    const WorkItem e1 = a.items[i1]; // items[n_items] is the end marker
-    S.item[0] = e0, S.item[1] = e1;
-    publish_next(e1);
+  }
+  // everything below reads what the previous launch wrote (Q, U, the work counter, the CFL mail)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if constexpr (!PLAIN)
+    wait_halo_item(a.items[blockIdx.x]); // the CTA's first item (all threads: see wait_halo_item)
+
+  // ---- part 2 (thread 0): the initial fill of both rings FIRST (so the rows travel while the rest is
+  // set up), the second work item, and this step's dt
+  if (t == 0)
+  {
+    const WorkItem e0 = S.item[0];
     // initial fill of both rings from the first item (>= 8 rows unless it is the CTA's only one)
     {
       const int x = tma_x0 + e0.strip * W - 2;
@@ -649,6 +603,14 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
       for (int n = 0; n < kNU && n < e0.j1 - e0.j0; ++n)
         stage_u(x + 2, e0.j0 + n, (uint32_t)n);
     }
+    // the second item comes from the counter; with a.persistent == 0 (degenerate grids: items of
+    // fewer than 8 rows) every CTA has just its one item
+    unsigned i1 = (unsigned)a.n_items;
+    if (a.persistent)
+      i1 = min(gridDim.x + atomicAdd(&sc->work_next, 1u), (unsigned)a.n_items);
+    const WorkItem e1 = a.items[i1]; // items[n_items] is the end marker
+    S.item[1] = e1;
+    publish_next(e1);
     // dt = CFL / max(inverse time-steps of the current state)   (ComputeDt.h:64): the hyperbolic
     // maximum was mailed to every rank by the last CTA of the previous final-stage sweep
     double dt = a.dt_host, hyp = 0.0, tc = p.epsilon, visc = p.epsilon;
@@ -1381,13 +1343,15 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
         last          = 1;
         sc->cta_done  = 0;
         sc->work_next = 0;
-        if (final_stage)
+        if (final_stage && !a.partial)
           hyp_slab = decode_ordered(atomicExch(&sc->inv_acc[1][0], FV2D_ENC_NEG_MAX));
       }
     }
     last     = __shfl_sync(0xffffffffu, last, 0);
     hyp_slab = __shfl_sync(0xffffffffu, hyp_slab, 0);
-    if (last && final_stage)
+    // (a partial launch - the streamed host path sweeps the slab row block by row block - leaves the
+    //  maximum in the accumulator and the clock alone: fv2d_stream.cu commits the step)
+    if (last && final_stage && !a.partial)
     {
       // The sweep's last CTA: the slab's maximum goes to every rank's mailbox (self included), one
       // lane per rank - the next step's dt is reduced on the device, no host round trip.  Then the
@@ -1521,9 +1485,23 @@ static cudaError_t launch_variant(const CUtensorMap &tmQ, const CUtensorMap &tmU
   static_assert(kNT != 256 || smem <= 115712, "two CTAs per SM need <= 113 KB of shared memory each");
   if (configure_only)
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  // persistent: CTA b starts on work item b and pulls the others from the device-wide counter
-  kern<<<a.n_ctas, kNT, smem, s>>>(tmQ, tmU, a);
-  return cudaGetLastError();
+  // persistent: CTA b starts on work item b and pulls the others from the device-wide counter.
+  // Programmatic stream serialization: the CTAs of this launch may become resident - and run the part
+  // of their prologue in front of griddepcontrol.wait - while the last CTAs of the previous kernel in
+  // the stream are still finishing.
+  static const bool pdl = std::getenv("FV2D_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim          = dim3((unsigned)a.n_ctas);
+  cfg.blockDim         = dim3(kNT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream           = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs    = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, tmQ, tmU, a);
 }
 
 template <bool PLM, int SOLVER, int GRAV, bool DIFF>

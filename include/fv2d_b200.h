@@ -182,10 +182,11 @@ int fv2d_integrate_mass_energy(fv2d_ctx *ctx, double *mass, double *energy);
  * (the multi-GPU contract is bitwise equality; main.cpp:62-84 has no counterpart). */
 int fv2d_state_hash(fv2d_ctx *ctx, uint64_t *hash);
 
-/* Measurement hooks (bench.py): when enabled, every sweep launch is bracketed by a pair of
- * CUDA events on the context's stream; fv2d_profile_read synchronises and returns the summed
- * sweep time, the number of sweep launches and the number of all kernel launches since
- * fv2d_profile_enable(ctx, 1). */
+/* Measurement hooks (bench.py).  fv2d_profile_enable(ctx, 1): every sweep launch is bracketed by a
+ * pair of CUDA events on the context's stream (which also keeps consecutive sweeps from overlapping
+ * their prologue with the previous sweep's tail); (ctx, 2): launches are only counted; (ctx, 0): off.
+ * fv2d_profile_read synchronises and returns the summed bracketed sweep time (0 unless mode 1), the
+ * number of sweep launches and the number of all kernel launches since the last fv2d_profile_enable. */
 int fv2d_profile_enable(fv2d_ctx *ctx, int on);
 int fv2d_profile_read(fv2d_ctx *ctx, double *sweep_ms, int64_t *sweep_launches, int64_t *total_launches);
 
@@ -223,6 +224,24 @@ int fv2d_debug_sweep_timing(fv2d_ctx *ctx, int64_t *out, int n);
  * NULL) receives the dt sequence.  Equivalent to the reference main.cpp:58-84 on a state
  * that lives on the host. */
 int fv2d_advance_host(fv2d_ctx *ctx, const double *hostQ_in, double *hostQ_out, int64_t nsteps, double *dts);
+
+/* One time step on a state that lives on the host, with the transfers overlapped: the loop body of
+ * main.cpp:62-84 (computeDt, UpdateFunctor::update, consToPrim, checkNegatives, t += dt) for a
+ * caller who holds Q in host memory (pinned memory for the overlap; pageable memory works, slower).
+ * dt_hint: the caller's idea of the time step of hostQ_in - normally *dt_next of the previous call
+ *   (UpdateFunctor::update takes dt as an argument too, Update.h:193) - or <= 0 for "none".
+ * With a hint on a single-slab forward-Euler context the state moves in row blocks: block b+1 is
+ * uploaded while block b is swept with dt_hint and block b-1 is downloaded (full-duplex PCIe), and
+ * the CFL time step of the uploaded state is evaluated on the way.  If it equals dt_hint bit for bit
+ * the step stands (*streamed = 1).  If not - or without a hint - the step is (re)done with the
+ * state's own time step, one transfer after the other (*streamed = 0).  Either way hostQ_out, *dt_used
+ * and *dt_next (the time step of the NEW state: the next call's hint) are the same bits: the hint
+ * changes how long the call takes, never what it returns.
+ * The time step is CFL / max(inverse time steps) as ComputeDt.h:18-65, with the sound speed in the
+ * fused sweep's arithmetic (<= 4 ulp from sqrt): *dt_used can differ from fv2d_compute_dt's in the last
+ * bits, like every dt of fv2d_run_steps after the first.  dt_used / dt_next / streamed may be NULL. */
+int fv2d_advance_host_stream(fv2d_ctx *ctx, const double *hostQ_in, double *hostQ_out, double dt_hint, double *dt_used,
+                             double *dt_next, int *streamed);
 
 /* ------------------------------------------------------------------ multi-GPU halo exchange
  * (no reference counterpart: the reference is single-device.)  Rows are exchanged over

@@ -15,6 +15,9 @@ from fv2d_b200 import capi  # noqa: E402
 wl = sys.argv[1] if len(sys.argv) > 1 else "kelvin_helmholtz_8192_plm_hllc"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 base, ov = bench.WORKLOADS[wl]
+ov = dict(ov)
+if len(sys.argv) > 3:  # rows of the slab (development: what one of N y-slabs sees)
+    ov["mesh.Ny"] = int(sys.argv[3])
 dev, run = capi.params_from_ini(ROOT / "settings" / base, ov)
 Q0 = capi.init_problem(dev, run)
 with capi.Context(dev, run.time_stepping, run.epsilon_reset_negative) as ctx:
