@@ -325,7 +325,12 @@ def native_arm(args):
         sampler.start()
         time.sleep(0.2)
     reps = []
-    for _ in range(max(1, args.reps)):
+    for k in range(max(1, args.reps)):
+        if k:
+            # repetitions are independent measurements: let the board's power average settle, or the
+            # later ones run into the power cap the earlier ones built up (that regime is what the
+            # `sustained` block below measures, on purpose)
+            time.sleep(args.rep_pause)
         reps.append(job.timed(args.steps))
     clocks = sampler.stop() if rank == 0 else None
     cfl_wait_main = job.cfl_wait_us
@@ -482,7 +487,7 @@ def native_arm(args):
                        "time_stepping": "euler" if job.run.time_stepping == 0 else "rk2",
                        "decomposition": f"{world} y-slab(s)", "l2_policy": "working set (3 arrays x %.2f GB) >> 126 MB L2"
                        % slab_gb, "host_init_s": round(host_init_s, 2),
-                       "repetitions": len(reps), "value_is": "median repetition",
+                       "repetitions": len(reps), "value_is": "median repetition", "idle_between_repetitions_s": args.rep_pause,
                        "ms_per_step_all_repetitions": [r[0] / args.steps for r in reps]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": frac,
                          "traffic": traffic, "kernel": "k_sweep (fused RK stage, persistent)", "peak_source": peak_src,
@@ -513,6 +518,7 @@ def main():
     ap.add_argument("--ny", type=int, default=0, help="override Ny (development only)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--reps", type=int, default=3, help="repetitions of the timed region; the median is reported")
+    ap.add_argument("--rep-pause", type=float, default=1.0, help="idle seconds between repetitions of the timed region")
     ap.add_argument("--sustained-steps", type=int, default=200, help="length of the sustained-regime region (0: skip)")
     ap.add_argument("--side-steps", type=int, default=20, help="timed steps of the strong_16384 / weak blocks")
     ap.add_argument("--no-scaling-blocks", action="store_true", help="skip the strong_16384 / weak blocks")

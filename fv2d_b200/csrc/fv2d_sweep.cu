@@ -139,11 +139,21 @@ __device__ __forceinline__ double dmin(double a, double b) { return (a < b) ? a 
 // on the integer pipe (one LOP3 + ISETP instead of a DMUL + DSETP on the half-rate fp64 pipe);
 // the two tests disagree only when a difference is exactly zero (the result is a zero either
 // way) or when the product underflows (|slope| < 1e-154).
+// The zero of an extremum clears only the HIGH word of the smaller difference (one select instead
+// of two): what is left is a denormal below 2^-1042, which the face-state fma (q +- s/2) rounds away
+// for every q that is not itself zero or denormal - and for q = 0 it adds less than 1e-314.
+#ifndef FV2D_MINMOD_HI
+#define FV2D_MINMOD_HI 1
+#endif
 __device__ __forceinline__ double minmod_f(double dL, double dR)
 {
   const double r = (fabs(dL) < fabs(dR)) ? dL : dR;
   const bool opp = (__double2hiint(dL) ^ __double2hiint(dR)) < 0;
+#if FV2D_MINMOD_HI
+  return __hiloint2double(opp ? 0 : __double2hiint(r), __double2loint(r));
+#else
   return opp ? 0.0 : r;
+#endif
 }
 
 // A face state in the frame of the face normal: n = normal velocity, t = tangential.

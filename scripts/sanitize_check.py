@@ -20,6 +20,7 @@ CASES = [("kh_plm_128x64", {"mesh.Nx": 600, "mesh.Ny": 150}), ("c91_64x32", {"me
          ("c91_plm_64x32", {"mesh.Nx": 260, "mesh.Ny": 40}), ("gresho_rk2_32", {"mesh.Nx": 280, "mesh.Ny": 70}),
          ("rt_fslp_32x96", {"mesh.Nx": 270, "mesh.Ny": 60}), ("blast_64", {"mesh.Nx": 300, "mesh.Ny": 64})]
 os.environ["FV2D_CHUNK_ROWS"] = "11"
+os.environ["FV2D_STREAM_ROWS"] = "16"
 os.environ["FV2D_MAX_CTAS"] = "3"  # few CTAs, several work items each: the cross-item TMA streams are exercised
 for name, ov in CASES:
     dev, run = capi.params_from_ini(load_golden(name).ini_path(), ov)
@@ -30,4 +31,10 @@ for name, ov in CASES:
         ctx.compute_dt()
         ctx.run_steps(2)
         U = ctx.download_U()
-    print(name, "finite:", bool(np.all(np.isfinite(U))), flush=True)
+    # the streamed host path: row blocks of 16 rows, partial sweeps, three streams
+    a, b, hint = Q0.copy(), np.empty_like(Q0), 0.0
+    with capi.Context(dev, run.time_stepping, run.epsilon_reset_negative) as ctx:
+        for _ in range(3):
+            _, hint, _ = ctx.advance_host_stream(a, b, hint)
+            a, b = b, a
+    print(name, "finite:", bool(np.all(np.isfinite(U))) and bool(np.all(np.isfinite(a))), flush=True)
