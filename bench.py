@@ -274,6 +274,13 @@ class Env:
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
         self.stream = torch.cuda.Stream()
         self.torch = torch
+        # one process per GPU: keep the host side (threads and the pages they touch first) on the NUMA
+        # node the GPU's PCIe root port belongs to
+        self.numa = None
+        if self.world > 1 and not os.environ.get("FV2D_NO_NUMA_BIND"):
+            from fv2d_b200 import multigpu
+
+            self.numa = multigpu.bind_to_gpu_numa_node(self.local_rank)
         os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // self.world)))
 
     def barrier(self):
@@ -485,7 +492,7 @@ def native_arm(args):
             "config": {"workload": args.workload, "Nx": Nx, "Ny": Ny, "riemann_solver": "hllc",
                        "reconstruction": {0: "pcm", 1: "pcm_wb", 2: "plm"}[job.dev.reconstruction],
                        "time_stepping": "euler" if job.run.time_stepping == 0 else "rk2",
-                       "decomposition": f"{world} y-slab(s)", "l2_policy": "working set (3 arrays x %.2f GB) >> 126 MB L2"
+                       "decomposition": f"{world} y-slab(s)", "host_numa_binding": env.numa, "l2_policy": "working set (3 arrays x %.2f GB) >> 126 MB L2"
                        % slab_gb, "host_init_s": round(host_init_s, 2),
                        "repetitions": len(reps), "value_is": "median repetition", "idle_between_repetitions_s": args.rep_pause,
                        "ms_per_step_all_repetitions": [r[0] / args.steps for r in reps]},

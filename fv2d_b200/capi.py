@@ -195,6 +195,7 @@ def lib() -> C.CDLL:
         "fv2d_debug_fp64_peak": [C.c_int, _dp],
         "fv2d_debug_sweep_timing": [_ctxp, C.POINTER(C.c_int64), C.c_int],
         "fv2d_debug_sync_wait": [_ctxp, _dp, _dp, _dp, C.c_int],
+        "fv2d_debug_stream_blocks": [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int)],
         "fv2d_debug_schedule": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int)],
     }
     for name, argtypes in sig.items():
@@ -286,6 +287,14 @@ def schedule_runs(Nx: int, Ny_local: int, num_sms: int = 148, neighbour_lo: bool
     n = C.c_int()
     _check(lib().fv2d_debug_schedule(Nx, Ny_local, num_sms, int(neighbour_lo), int(neighbour_hi), buf, 65536, C.byref(n)))
     return [(buf[2 * k], buf[2 * k + 1]) for k in range(n.value)]
+
+
+def stream_blocks(Ny: int, Ng: int = 2, block_rows: int = 0):
+    """Row blocks [(up0, up1, sw0, sw1), ...] of the streamed host path (host logic, no GPU needed)."""
+    buf = (C.c_int32 * (4 * 65536))()
+    n = C.c_int()
+    _check(lib().fv2d_debug_stream_blocks(Ny, Ng, block_rows, buf, 65536, C.byref(n)))
+    return [tuple(buf[4 * k + i] for i in range(4)) for k in range(n.value)]
 
 
 def fp64_peak(device: int = 0) -> float:

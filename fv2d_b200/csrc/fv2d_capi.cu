@@ -1439,29 +1439,49 @@ static int copy_rows(fv2d_ctx *c, double *dense, double *host, int r0, int r1, b
   return FV2D_OK;
 }
 
-// Row blocks of the streamed path and the work table of each block's partial sweep.  Block b brings
-// up domain rows [up0, up1); the rows whose 2-row stencil is complete by then, [sw0, sw1), are swept.
+// Row blocks of the streamed path (pure host logic, also behind fv2d_debug_stream_blocks).  Block b
+// brings up domain rows [up0, up1) (array row indices); the rows whose 2-row stencil is complete by
+// then, [sw0, sw1), are swept: everything up to 2 rows below the block's upper edge, the last block
+// up to the top of the domain (its upper neighbours are ghost rows, filled on the device).
+static std::vector<fv2d_ctx::StreamBlock> stream_blocks(int Ny, int jbeg, int block_rows)
+{
+  const int B = std::max(16, block_rows), jend = jbeg + Ny;
+  const int nb = std::max(1, Ny / B);
+  std::vector<fv2d_ctx::StreamBlock> blk((size_t)nb);
+  for (int b = 0; b < nb; ++b)
+  {
+    fv2d_ctx::StreamBlock &k = blk[b];
+    k.up0 = jbeg + b * B;
+    k.up1 = (b == nb - 1) ? jend : jbeg + (b + 1) * B;
+    k.sw0 = (b == 0) ? jbeg : blk[b - 1].sw1;
+    k.sw1 = (b == nb - 1) ? jend : k.up1 - 2;
+    k.item_off = k.n_items = k.n_ctas = k.persistent = 0;
+  }
+  return blk;
+}
+static int stream_block_rows()
+{
+  if (const char *e = std::getenv("FV2D_STREAM_ROWS"))
+    if (std::atoi(e) >= 16)
+      return std::atoi(e);
+  return 256;
+}
+
+// ... and the work table of each block's partial sweep
 static int ensure_stream_blocks(fv2d_ctx *c)
 {
   if (c->sblocks)
     return FV2D_OK;
   const fv2d_device_params &p = c->kp.p;
-  int B = 256;
-  if (const char *e = std::getenv("FV2D_STREAM_ROWS"))
-    if (std::atoi(e) >= 16)
-      B = std::atoi(e);
-  const int nb = std::max(1, p.Ny / B);
+  const std::vector<fv2d_ctx::StreamBlock> plan = stream_blocks(p.Ny, p.jbeg, stream_block_rows());
+  const int nb = (int)plan.size();
   const int W = sweep_strip_width(), nstrips = (p.Nx + W - 1) / W, slots = 2 * c->num_sms;
   std::vector<WorkItem> items;
   fv2d_ctx::StreamBlock *blk = new fv2d_ctx::StreamBlock[nb];
-  bool ok = true;
   for (int b = 0; b < nb; ++b)
   {
     fv2d_ctx::StreamBlock &k = blk[b];
-    k.up0 = p.jbeg + b * B;
-    k.up1 = (b == nb - 1) ? p.jend : p.jbeg + (b + 1) * B;
-    k.sw0 = (b == 0) ? p.jbeg : blk[b - 1].sw1;
-    k.sw1 = (b == nb - 1) ? p.jend : k.up1 - 2;
+    k = plan[b];
     const std::vector<std::pair<int, int>> runs = schedule_runs(k.sw1 - k.sw0, nstrips, slots, false, false);
     k.item_off = (int)items.size();
     int min_rows = k.sw1 - k.sw0;
@@ -1474,13 +1494,7 @@ static int ensure_stream_blocks(fv2d_ctx *c)
     k.n_items    = (int)items.size() - k.item_off;
     k.persistent = min_rows >= 8;
     k.n_ctas     = k.persistent ? std::min(k.n_items, slots) : k.n_items;
-    ok           = ok && k.sw1 > k.sw0;
     items.push_back(WorkItem{0, -1, -1, 0}); // end marker of this block's table
-  }
-  if (!ok)
-  {
-    delete[] blk;
-    return arg_fail("streamed path: grid too small for the row blocks");
   }
   FV2D_CUDA(cudaMalloc(&c->sitems_dev, items.size() * sizeof(WorkItem)));
   FV2D_CUDA(cudaMemcpyAsync(c->sitems_dev, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, c->stream));
@@ -1495,6 +1509,17 @@ static int ensure_stream_blocks(fv2d_ctx *c)
     FV2D_CUDA(cudaEventCreateWithFlags(&c->s_ev[k], cudaEventDisableTiming));
   c->sblocks   = blk;
   c->n_sblocks = nb;
+  return FV2D_OK;
+}
+
+int fv2d_debug_stream_blocks(int Ny, int Ng, int block_rows, int32_t *blocks, int max_blocks, int *n_blocks)
+{
+  if (Ny < 1 || Ng < 0 || !blocks || !n_blocks)
+    return arg_fail("fv2d_debug_stream_blocks: bad arguments");
+  const auto b = stream_blocks(Ny, Ng, block_rows > 0 ? block_rows : stream_block_rows());
+  *n_blocks    = (int)b.size();
+  for (int k = 0; k < (int)b.size() && k < max_blocks; ++k)
+    blocks[4 * k] = b[k].up0, blocks[4 * k + 1] = b[k].up1, blocks[4 * k + 2] = b[k].sw0, blocks[4 * k + 3] = b[k].sw1;
   return FV2D_OK;
 }
 

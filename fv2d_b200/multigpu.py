@@ -65,3 +65,43 @@ def connect_local(ctxs) -> None:
     handles = b"".join(c.halo_export() for c in ctxs)
     for c in ctxs:
         c.halo_connect(handles, len(ctxs))
+
+
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pins this process to the CPUs of the NUMA node the GPU hangs off, so that the host arrays it
+    allocates from here on (first touch, pinned or not) live in the memory next to the GPU's PCIe root
+    port.  One process per GPU on a multi-socket box otherwise sends half of the host<->device traffic
+    across the socket interconnect.  Best effort: returns what it did, never raises."""
+    import os
+
+    info = {"device": device_index, "numa_node": None, "cpus": None}
+    try:
+        import torch
+
+        prop = torch.cuda.get_device_properties(device_index)
+        if hasattr(prop, "pci_bus_id"):
+            bdf = f"{getattr(prop, 'pci_domain_id', 0):04x}:{prop.pci_bus_id:02x}:{getattr(prop, 'pci_device_id', 0):02x}.0"
+        else:  # older torch: ask NVML (same enumeration order unless CUDA_VISIBLE_DEVICES reorders)
+            import pynvml
+
+            pynvml.nvmlInit()
+            bus_id = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device_index)).busId
+            bus_id = bus_id.decode() if isinstance(bus_id, bytes) else bus_id
+            bdf = bus_id.lower()[-12:]  # "00000000:04:00.0" -> "0000:04:00.0"
+        path = f"/sys/bus/pci/devices/{bdf}/numa_node"
+        node = int(open(path).read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        cpulist = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info["cpus"] = len(cpus)
+    except Exception as e:  # noqa: BLE001 - best effort by design
+        info["error"] = str(e)
+    return info

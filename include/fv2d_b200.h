@@ -214,6 +214,12 @@ int fv2d_debug_sync_wait(fv2d_ctx *ctx, double *last_wait_us, double *total_wait
 int fv2d_debug_schedule(int Nx, int Ny_local, int num_sms, int neighbour_lo, int neighbour_hi, int32_t *runs, int max_runs,
                         int *n_runs);
 
+/* Test hook (host only, needs no GPU): the row blocks in which fv2d_advance_host_stream moves a slab of
+ * Ny rows with Ng ghost rows a side (block_rows <= 0: the default, 256, or FV2D_STREAM_ROWS).  blocks
+ * receives up to max_blocks quadruples (up0, up1, sw0, sw1) of array row indices: block b uploads rows
+ * [up0, up1) and then sweeps rows [sw0, sw1); *n_blocks the number of blocks. */
+int fv2d_debug_stream_blocks(int Ny, int Ng, int block_rows, int32_t *blocks, int max_blocks, int *n_blocks);
+
 /* Development hook (only in library variants built with -DFV2D_TIMING; FV2D_ERR_ARG otherwise):
  * per CTA of the last sweep, 4 values: clock cycles outside the row loops, inside them, work items
  * processed, total. */

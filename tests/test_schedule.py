@@ -44,3 +44,23 @@ def test_runs_of_a_round_are_equal():
     per_round = (296 + 8) // 17
     for r in range(0, len(heights) - per_round, per_round):
         assert len(set(heights[r:r + per_round])) == 1, (r, heights[r:r + per_round])
+
+
+@pytest.mark.parametrize("Ny,Ng,rows", [(8192, 2, 0), (8192, 2, 128), (64, 2, 16), (100, 3, 16), (5, 2, 16), (1000, 2, 256),
+                                        (16384, 2, 512), (33, 2, 16), (31, 2, 16)])
+def test_stream_blocks_cover_the_slab_and_respect_the_stencil(Ny, Ng, rows):
+    """Row blocks of fv2d_advance_host_stream (fv2d_capi.cu: stream_blocks): uploads tile the domain rows,
+    sweeps tile them too, and a block never sweeps a row whose upper neighbours (2 rows) are not
+    resident yet - except the last block, whose upper neighbours are ghost rows."""
+    blocks = capi.stream_blocks(Ny, Ng, rows)
+    jbeg, jend = Ng, Ng + Ny
+    assert blocks[0][0] == jbeg and blocks[0][2] == jbeg and blocks[-1][1] == jend and blocks[-1][3] == jend
+    for (u0, u1, s0, s1), (v0, v1, t0, t1) in zip(blocks, blocks[1:]):
+        assert u1 == v0 and s1 == t0
+    for k, (u0, u1, s0, s1) in enumerate(blocks):
+        assert u1 > u0 and s1 > s0
+        if k < len(blocks) - 1:
+            assert s1 + 2 <= u1          # rows s1, s1 + 1 (read by row s1 - 1) have arrived
+        assert s0 - 2 >= jbeg - Ng        # rows below come from earlier blocks or are low ghost rows
+    B = rows if rows > 0 else 256
+    assert len(blocks) == max(1, Ny // max(16, B))
