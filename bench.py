@@ -60,7 +60,7 @@ class ClockSampler:
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,enforced.power.limit")
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
@@ -84,7 +84,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons, pw = [], [], set(), []
+        sm, mx, reasons, pw, limit = [], [], set(), [], None
         for l in self.lines:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 8:
@@ -98,8 +98,13 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
+            if len(f) > 8:
+                try:
+                    limit = float(f[8])
+                except ValueError:
+                    pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "power_limit_w": limit, "samples": len(sm), "reasons": sorted(reasons)}
 
 
 def write_ini(workload: str, extra=None) -> str:

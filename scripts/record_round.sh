@@ -1,8 +1,11 @@
 #!/bin/bash
-# round-2 GPU call Z1 (1 GPU): GPU suite, smoke, sanitizer, bench records of the shipped HEAD, ncu evidence
+# Developer tool (GPU box, 1 GPU): the round's record of the shipped HEAD -> gpurun_out/<tag>_*: GPU suite, smoke,
+# compute-sanitizer, the bench lines (driver-like and default), the reference arm, the other workloads, the ncu launch
+# list and `ncu --set full` captures of the sweep, full-size parity against the reference binary.
+#   scripts/record_round.sh [tag]
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-T=r2v8
+T=${1:-r2v8}
 timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -4 | tee gpurun_out/${T}_pytest_gpu_1gpu.txt
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | grep -v WARNING | tail -3
 echo "== racecheck"; timeout 900 compute-sanitizer --tool racecheck python scripts/sanitize_check.py 2>&1 | grep -v WARNING | tail -9 | tee gpurun_out/${T}_sanitizer_racecheck.txt
@@ -37,3 +40,5 @@ for wl in kelvin_helmholtz_8192_plm_hllc c91_8192_pcm_hllc_tc_visc; do
   tail -1 gpurun_out/${T}_ncu_$wl.log | cut -c1-160
 done
 ls -la gpurun_out/${T}*.ncu-rep
+echo "== full-size parity against the reference binary"
+timeout 1500 python scripts/parity_fullsize.py --out gpurun_out/${T}_parity_fullsize.json 2>&1 | grep -v WARNING | tail -12

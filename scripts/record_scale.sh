@@ -1,9 +1,10 @@
 #!/bin/bash
-# round-2 GPU call Z2 (N GPUs): multi-GPU bitwise tests (N = 8 only) + the driver-like bench line at N
+# Developer tool (GPU box with N GPUs): multi-GPU bitwise tests (N = 8 only) + the driver-like bench line at N
+#   scripts/record_scale.sh N [tag]
 N=${1:-8}
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-T=r2v8
+T=${2:-r2v8}
 if [ "$N" == "8" ]; then
   timeout 600 python -m pytest tests/test_gpu_multigpu.py -q 2>&1 | tail -3 | tee gpurun_out/${T}_pytest_multigpu_8gpu.txt
 fi

@@ -143,3 +143,30 @@ def test_negative_counters_survive_a_rejected_speculation():
             out.append((a.copy(), du, dn2, ctx.negative_counts()))
     assert np.array_equal(out[0][0], out[1][0], equal_nan=True) and out[0][1:3] == out[1][1:3]
     assert out[0][3] == out[1][3] and sum(out[0][3]) > 0
+
+
+@pytest.mark.parametrize("bx", ["absorbing", "reflecting", "periodic"])
+@pytest.mark.parametrize("by", ["absorbing", "reflecting", "periodic"])
+@pytest.mark.parametrize("ng", [2, 3])
+def test_every_boundary_combination_and_ghost_depth(bx, by, ng):
+    """The streamed path fills the ghost cells of the rows it uploads itself (low y-ghost rows with the
+    first block - a periodic boundary needs the LAST domain rows for them - high ones with the last):
+    all nine boundary combinations, Nghosts 2 and 3, on a grid of several row blocks, against the
+    serial route of the same entry point (bitwise) and against the resident fused run (tolerance)."""
+    g = load_golden("blast_64")
+    ov = {"run.boundaries_x": bx, "run.boundaries_y": by, "mesh.Nghosts": ng, "mesh.Nx": 300, "mesh.Ny": 70}
+    dev, run = capi.params_from_ini(g.ini_path(), ov)
+    Q0 = capi.init_problem(dev, run)
+    n = 4
+    ref = _chain(dev, run, Q0, n, "none")
+    got = _chain(dev, run, Q0, n, "good")
+    assert got[3] == [False] + [True] * (n - 1)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and np.array_equal(got[4][3], ref[4][3])
+    with capi.Context(dev, run.time_stepping, run.epsilon_reset_negative) as ctx:
+        ctx.upload_Q(Q0)
+        ctx.prim_to_cons()
+        ctx.compute_dt()
+        ctx.run_steps(n)
+        Qres, hres = ctx.download_Q(), ctx.dt_history(n)
+    assert np.max(np.abs(got[1] - hres) / hres) <= TOL_DT
+    assert rel_l1(got[0], Qres) <= TOL_L1  # whole arrays, ghost cells included
