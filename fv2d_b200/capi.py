@@ -195,6 +195,7 @@ def lib() -> C.CDLL:
         "fv2d_debug_fp64_peak": [C.c_int, _dp],
         "fv2d_debug_sweep_timing": [_ctxp, C.POINTER(C.c_int64), C.c_int],
         "fv2d_debug_sync_wait": [_ctxp, _dp, _dp, _dp, C.c_int],
+        "fv2d_device_count": [C.POINTER(C.c_int)],
         "fv2d_debug_stream_blocks": [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int)],
         "fv2d_debug_schedule": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int)],
     }
@@ -295,6 +296,12 @@ def stream_blocks(Ny: int, Ng: int = 2, block_rows: int = 0):
     n = C.c_int()
     _check(lib().fv2d_debug_stream_blocks(Ny, Ng, block_rows, buf, 65536, C.byref(n)))
     return [tuple(buf[4 * k + i] for i in range(4)) for k in range(n.value)]
+
+
+def device_count() -> int:
+    n = C.c_int()
+    _check(lib().fv2d_device_count(C.byref(n)))
+    return n.value
 
 
 def fp64_peak(device: int = 0) -> float:

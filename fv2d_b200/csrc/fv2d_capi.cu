@@ -509,6 +509,15 @@ extern "C" {
 const char *fv2d_last_error(void) { return g_last_error.c_str(); }
 int fv2d_abi_version(void) { return 1; }
 
+int fv2d_device_count(int *count)
+{
+  if (!count)
+    return arg_fail("null output");
+  *count = 0;
+  FV2D_CUDA(cudaGetDeviceCount(count));
+  return FV2D_OK;
+}
+
 int fv2d_params_from_ini(const char *ini_path, const char *overrides, fv2d_device_params *dev, fv2d_run_params *run)
 {
   if (!ini_path || !dev || !run)
@@ -1496,17 +1505,36 @@ static int ensure_stream_blocks(fv2d_ctx *c)
     k.n_ctas     = k.persistent ? std::min(k.n_items, slots) : k.n_items;
     items.push_back(WorkItem{0, -1, -1, 0}); // end marker of this block's table
   }
-  FV2D_CUDA(cudaMalloc(&c->sitems_dev, items.size() * sizeof(WorkItem)));
-  FV2D_CUDA(cudaMemcpyAsync(c->sitems_dev, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, c->stream));
-  FV2D_CUDA(cudaStreamSynchronize(c->stream));
+  // all or nothing: a failed allocation (the two dense copies are as large as Q) leaves the context as
+  // it was, and the caller falls back to the serial route
   const size_t dense_bytes = (size_t)4 * p.Nty * p.Ntx * sizeof(double);
-  FV2D_CUDA(cudaMalloc(&c->dense_in, dense_bytes));
-  FV2D_CUDA(cudaMalloc(&c->dense_out, dense_bytes));
-  FV2D_CUDA(cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking));
-  FV2D_CUDA(cudaStreamCreateWithFlags(&c->s_dn, cudaStreamNonBlocking));
-  c->s_ev = new cudaEvent_t[2 * nb + 2];
+  WorkItem *items_dev = nullptr;
+  double *din = nullptr, *dout = nullptr;
+  cudaError_t e = cudaMalloc(&items_dev, items.size() * sizeof(WorkItem));
+  if (e == cudaSuccess)
+    e = cudaMalloc(&din, dense_bytes);
+  if (e == cudaSuccess)
+    e = cudaMalloc(&dout, dense_bytes);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(items_dev, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess)
+  {
+    cudaFree(items_dev), cudaFree(din), cudaFree(dout);
+    delete[] blk;
+    cudaGetLastError(); // the error is reported, not sticky
+    return cuda_fail(e, "streamed path: staging buffers", __FILE__, __LINE__);
+  }
+  if (!c->s_up)
+    FV2D_CUDA(cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking));
+  if (!c->s_dn)
+    FV2D_CUDA(cudaStreamCreateWithFlags(&c->s_dn, cudaStreamNonBlocking));
+  cudaEvent_t *ev = new cudaEvent_t[2 * nb + 2];
   for (int k = 0; k < 2 * nb + 2; ++k)
-    FV2D_CUDA(cudaEventCreateWithFlags(&c->s_ev[k], cudaEventDisableTiming));
+    cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+  c->sitems_dev = items_dev, c->dense_in = din, c->dense_out = dout;
+  c->s_ev      = ev;
   c->sblocks   = blk;
   c->n_sblocks = nb;
   return FV2D_OK;
@@ -1559,13 +1587,13 @@ int fv2d_advance_host_stream(fv2d_ctx *c, const double *hostQ_in, double *hostQ_
 
   // Speculation needs: a dt to speculate with, a single slab (the check of the hint is a local
   // decision), one sweep per step, and ghost cells the sweep can write itself.
-  const bool speculate = dt_hint > 0.0 && c->nranks == 1 && c->time_stepping != FV2D_TS_RK2 && c->fold_ok &&
-                         !std::getenv("FV2D_STREAM_OFF");
+  bool speculate = dt_hint > 0.0 && c->nranks == 1 && c->time_stepping != FV2D_TS_RK2 && c->fold_ok &&
+                   !std::getenv("FV2D_STREAM_OFF");
+  if (speculate && ensure_stream_blocks(c) != FV2D_OK)
+    speculate = false; // no room for the staging copies: the serial route needs none
   bool need_plain_step = true;
   if (speculate)
   {
-    if ((rc = ensure_stream_blocks(c)))
-      return rc;
     const int cur = c->cur, nxt = cur ^ 1, nb = c->n_sblocks;
     cudaEvent_t *ev = c->s_ev;
     // the copy streams start after whatever the context's stream still has in flight

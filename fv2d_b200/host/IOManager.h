@@ -56,6 +56,19 @@ public:
     saveSolutionHost(makeSnapshotConfig(params), h, iteration, t, force_file_truncation);
   }
 
+  // the same on a host array (what the multi-GPU driver assembles from its slabs)
+  void saveSolution(const HostArray &h, int iteration, real_t t)
+  {
+    saveSolutionHost(makeSnapshotConfig(params), h, iteration, t, force_file_truncation);
+  }
+  RestartInfo loadSnapshot(HostArray &h)
+  {
+    const RestartInfo info = loadSnapshotHost(makeSnapshotConfig(params), h, force_file_truncation);
+    if (force_file_truncation)
+      saveSolution(h, info.iteration, info.time);
+    return info;
+  }
+
   RestartInfo loadSnapshot(Array &Q)
   {
     HostArray h(device_params.Nty, device_params.Ntx);

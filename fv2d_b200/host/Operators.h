@@ -15,10 +15,14 @@
 // Errors of the C ABI become std::runtime_error, like the reference's configuration errors.
 #pragma once
 
+#include <algorithm>
+#include <array>
 #include <iostream>
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/fv2d_b200.h"
 #include "Init.h"
@@ -206,5 +210,137 @@ inline void checkNegatives(const Array &Q, const Params &)
   check(fv2d_check_negatives(Q.ctx(), c), "checkNegatives");
   printNegatives(std::cout, c);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU: the grid as y-slabs, one device context per slab, all driven by this one host
+// process (no counterpart in the reference, which is single-device: main.cpp:13-101).  After
+// connect() the slabs exchange their ghost rows and the global CFL maximum from inside the sweep
+// kernels over peer mappings: a step is one asynchronous launch per slab, no host round trip.
+class SlabSet
+{
+public:
+  Params params;
+  std::vector<fv2d_ctx *> ctx;
+
+  // slab r runs on device first_device + (r mod ndevices)
+  SlabSet(const Params &p, int nslabs, int first_device, int ndevices) : params(p)
+  {
+    if (nslabs < 1 || ndevices < 1)
+      throw std::runtime_error("SlabSet: need at least one slab and one device");
+    ctx.assign(size_t(nslabs), nullptr);
+    for (int r = 0; r < nslabs; ++r)
+      check(fv2d_ctx_create_slab(&params.device_params, params.time_stepping, params.epsilon_reset_negative,
+                                 first_device + r % ndevices, r, nslabs, &ctx[size_t(r)]),
+            "fv2d_ctx_create_slab");
+    std::vector<unsigned char> handles(size_t(nslabs) * FV2D_IPC_HANDLE_BYTES);
+    for (int r = 0; r < nslabs; ++r)
+      check(fv2d_halo_export(ctx[size_t(r)], handles.data() + size_t(r) * FV2D_IPC_HANDLE_BYTES), "fv2d_halo_export");
+    for (int r = 0; r < nslabs; ++r)
+      check(fv2d_halo_connect(ctx[size_t(r)], handles.data(), nslabs), "fv2d_halo_connect");
+  }
+  ~SlabSet()
+  {
+    for (fv2d_ctx *c : ctx)
+      if (c)
+        fv2d_sync(c);
+    for (fv2d_ctx *c : ctx)
+      fv2d_ctx_destroy(c);
+  }
+  SlabSet(const SlabSet &)            = delete;
+  SlabSet &operator=(const SlabSet &) = delete;
+
+  // rows [first, first + n) of the global array (ghost rows included) that slab r holds
+  void rowsOf(size_t r, int &first, int &n) const
+  {
+    int64_t g[6];
+    check(fv2d_ctx_geometry(ctx[r], g), "fv2d_ctx_geometry");
+    first = int(g[3]);
+    n     = int(g[1]);
+  }
+  // global host array -> slabs (each with its ghost rows, taken from the neighbours' rows) and back
+  // (the result's ghost rows are the outer slabs' own)
+  void upload(const HostArray &h) const
+  {
+    for (size_t r = 0; r < ctx.size(); ++r)
+    {
+      int first, n;
+      rowsOf(r, first, n);
+      HostArray s(n, h.Ntx);
+      for (int f = 0; f < Nfields; ++f)
+        std::copy(&h(first, 0, f), &h(first, 0, f) + size_t(n) * h.Ntx, &s(0, 0, f));
+      check(fv2d_upload_Q(ctx[r], s.data.data()), "upload");
+    }
+  }
+  void download(HostArray &h) const
+  {
+    const int Ng = params.device_params.Ng;
+    for (size_t r = 0; r < ctx.size(); ++r)
+    {
+      int first, n;
+      rowsOf(r, first, n);
+      HostArray s(n, h.Ntx);
+      check(fv2d_download_Q(ctx[r], s.data.data()), "download");
+      const int lo = (r == 0) ? 0 : Ng, hi = (r + 1 == ctx.size()) ? n : n - Ng; // own rows (+ the outer ghosts)
+      for (int f = 0; f < Nfields; ++f)
+        std::copy(&s(lo, 0, f), &s(lo, 0, f) + size_t(hi - lo) * h.Ntx, &h(first + lo, 0, f));
+    }
+  }
+  void primToCons() const
+  {
+    for (fv2d_ctx *c : ctx)
+      check(fv2d_prim_to_cons(c), "primToCons");
+  }
+  void setTime(real_t t) const
+  {
+    for (fv2d_ctx *c : ctx)
+      check(fv2d_set_time(c, t), "set_time");
+  }
+  // ComputeDtFunctor::computeDt over all slabs.  fv2d_compute_dt is collective and synchronises the
+  // host, so every slab gets its own host thread for the call.
+  real_t computeDt(double inv[3]) const
+  {
+    std::vector<double> dt(ctx.size(), 0.0);
+    std::vector<std::string> err(ctx.size());
+    std::vector<std::array<double, 3>> iv(ctx.size());
+    std::vector<std::thread> th;
+    for (size_t r = 0; r < ctx.size(); ++r)
+      th.emplace_back([&, r] {
+        if (fv2d_compute_dt(ctx[r], &dt[r], iv[r].data()) != FV2D_OK)
+          err[r] = fv2d_last_error();
+      });
+    for (auto &t : th)
+      t.join();
+    for (const auto &e : err)
+      if (!e.empty())
+        throw std::runtime_error("computeDt: " + e);
+    for (int k = 0; k < 3; ++k)
+      inv[k] = iv[0][size_t(k)];
+    return dt[0];
+  }
+  // one fused step on every slab (asynchronous: the slabs' sweeps run side by side)
+  void fusedStepDeviceDt() const
+  {
+    for (fv2d_ctx *c : ctx)
+      check(fv2d_step_device_dt(c), "fused_step_device_dt");
+  }
+  void negativeCounts(uint64_t total[3]) const
+  {
+    total[0] = total[1] = total[2] = 0;
+    for (fv2d_ctx *c : ctx)
+    {
+      uint64_t k[3];
+      check(fv2d_get_negative_counts(c, k, 1), "negative counts");
+      for (int i = 0; i < 3; ++i)
+        total[i] += k[i];
+    }
+  }
+  void getTime(real_t &t, real_t &next_dt) const { check(fv2d_get_time(ctx[0], &t, &next_dt, nullptr), "get_time"); }
+  void invDt(double inv[3]) const { check(fv2d_get_inv_dt(ctx[0], inv), "get_inv_dt"); }
+  void sync() const
+  {
+    for (fv2d_ctx *c : ctx)
+      check(fv2d_sync(c), "sync");
+  }
+};
 
 } // namespace fv2d

@@ -86,6 +86,10 @@ int fv2d_io_save_solution(const fv2d_device_params *dev, const fv2d_run_params *
 int fv2d_io_load_snapshot(const fv2d_device_params *dev, const fv2d_run_params *run, double *hostQ, double *time,
                           int *iteration, int *force_file_truncation);
 
+/* Number of CUDA devices visible to this process (what a host driver without a CUDA dependency of its
+ * own needs to place the y-slabs of a multi-GPU run). */
+int fv2d_device_count(int *count);
+
 /* ------------------------------------------------------------------ context */
 
 /* Allocates Q and U (zero-filled, like Kokkos Views: main.cpp:33-34) on CUDA device

@@ -218,3 +218,35 @@ def test_advance_host_on_slabs_round_trips_complete_arrays():
             c.sync()
         for c in ctxs:
             c.close()
+
+
+def test_cpp_host_driver_on_real_gpus(tmp_path):
+    """fv2d_b200_main --gpus N with one GPU per slab (no device sharing) on a grid large enough for
+    every slab to run many CTAs: the snapshot files are byte for byte the single-GPU run's."""
+    import subprocess
+    from pathlib import Path
+
+    ndev = _ngpu()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = Path(__file__).resolve().parents[1]
+    exe = root / "fv2d_b200" / "fv2d_b200_main"
+    if not exe.exists():
+        subprocess.run(["make", "driver"], cwd=root, check=True, capture_output=True)
+    ini = tmp_path / "kh.ini"
+    text = Path(load_golden("kh_plm_128x64").ini_path()).read_text().replace("Nx=128", "Nx=2048").replace("Ny=64", "Ny=1024")
+    assert "Nx=2048" in text and "Ny=1024" in text
+    ini.write_text(text)
+    out = {}
+    for n in (1, min(ndev, 8)):
+        d = tmp_path / f"n{n}"
+        d.mkdir()
+        r = subprocess.run([str(exe), str(ini), "--max-steps", "25", "--quiet"] + (["--gpus", str(n)] if n > 1 else []), cwd=d,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        out[n] = {p.name: p.read_bytes() for p in sorted(d.iterdir()) if p.suffix in (".h5", ".xmf")}
+        assert any(k.endswith(".h5") for k in out[n])
+    a1, an = out[1], out[min(ndev, 8)]
+    assert a1.keys() == an.keys()
+    for k in a1:
+        assert a1[k] == an[k], k

@@ -215,6 +215,36 @@ def test_advance_host_equals_resident_run():
     assert rel_l1(O.domain(dev, Qout), g.QN) <= TOL_L1
 
 
+@pytest.mark.parametrize("name", ["kh_plm_128x64", "c91_plm_64x32", "blast_rk2_plm_48"])
+def test_cpp_host_driver_on_y_slabs_is_bitwise_the_single_gpu_run(tmp_path, name):
+    """fv2d_b200_main <ini> --gpus N: the C++17 driver on N y-slabs (SlabSet in host/Operators.h, one
+    process, one context per slab; the slabs share devices when the box has fewer GPUs than slabs).
+    Same log lines, and the snapshot files are byte for byte the single-GPU run's."""
+    exe = ROOT / "fv2d_b200" / "fv2d_b200_main"
+    if not exe.exists():
+        subprocess.run(["make", "driver"], cwd=ROOT, check=True, capture_output=True)
+    g = load_golden(name)
+    ndev = capi.device_count()
+    runs = {}
+    for n in (1, 2, 3):
+        d = tmp_path / f"n{n}"
+        d.mkdir()
+        cmd = [str(exe), g.ini_path(), "--max-steps", "10"]
+        if n > 1:
+            cmd += ["--gpus", str(n)] + (["--share-devices"] if ndev < n else [])
+        r = subprocess.run(cmd, cwd=d, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        files = {p.name: p.read_bytes() for p in sorted(d.iterdir()) if p.suffix in (".h5", ".xmf")}
+        assert any(k.endswith(".h5") for k in files)
+        runs[n] = ([l for l in r.stdout.splitlines() if l.startswith(("Computing dts", " - Saving", "Time at end", "-->"))], files)
+    for n in (2, 3):
+        assert runs[n][0] == runs[1][0], (n, runs[n][0], runs[1][0])
+        # run.h5 / run.xmf (or the per-snapshot files of run.multiple_outputs): the same bytes
+        assert runs[n][1].keys() == runs[1][1].keys()
+        for k in runs[1][1]:
+            assert runs[n][1][k] == runs[1][1][k], (n, k)
+
+
 def test_cpp_host_driver_runs_the_reference_loop(tmp_path):
     """fv2d_b200_main <ini>: the C++17 mirror of main.cpp, fused and --unfused."""
     exe = ROOT / "fv2d_b200" / "fv2d_b200_main"
