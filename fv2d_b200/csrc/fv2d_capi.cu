@@ -1587,8 +1587,9 @@ int fv2d_advance_host_stream(fv2d_ctx *c, const double *hostQ_in, double *hostQ_
 
   // Speculation needs: a dt to speculate with, a single slab (the check of the hint is a local
   // decision), one sweep per step, and ghost cells the sweep can write itself.
+  // (in place - hostQ_out == hostQ_in - the redo after a rejected hint would find its input overwritten)
   bool speculate = dt_hint > 0.0 && c->nranks == 1 && c->time_stepping != FV2D_TS_RK2 && c->fold_ok &&
-                   !std::getenv("FV2D_STREAM_OFF");
+                   hostQ_in != hostQ_out && !std::getenv("FV2D_STREAM_OFF");
   if (speculate && ensure_stream_blocks(c) != FV2D_OK)
     speculate = false; // no room for the staging copies: the serial route needs none
   bool need_plain_step = true;

@@ -249,7 +249,8 @@ int fv2d_advance_host(fv2d_ctx *ctx, const double *hostQ_in, double *hostQ_out, 
  * changes how long the call takes, never what it returns.
  * The time step is CFL / max(inverse time steps) as ComputeDt.h:18-65, with the sound speed in the
  * fused sweep's arithmetic (<= 4 ulp from sqrt): *dt_used can differ from fv2d_compute_dt's in the last
- * bits, like every dt of fv2d_run_steps after the first.  dt_used / dt_next / streamed may be NULL. */
+ * bits, like every dt of fv2d_run_steps after the first.  dt_used / dt_next / streamed may be NULL.
+ * hostQ_out may be hostQ_in (in place): the call then takes the serial route. */
 int fv2d_advance_host_stream(fv2d_ctx *ctx, const double *hostQ_in, double *hostQ_out, double dt_hint, double *dt_used,
                              double *dt_next, int *streamed);
 

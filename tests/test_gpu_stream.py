@@ -170,3 +170,17 @@ def test_every_boundary_combination_and_ghost_depth(bx, by, ng):
         Qres, hres = ctx.download_Q(), ctx.dt_history(n)
     assert np.max(np.abs(got[1] - hres) / hres) <= TOL_DT
     assert rel_l1(got[0], Qres) <= TOL_L1  # whole arrays, ghost cells included
+
+
+def test_in_place_call_takes_the_serial_route_and_gives_the_same_bits():
+    g = load_golden("kh_plm_128x64")
+    dev, run = capi.params_from_ini(g.ini_path())
+    Q0 = capi.init_problem(dev, run)
+    ref = _chain(dev, run, Q0, 3)
+    a = Q0.copy()
+    with capi.Context(dev, run.time_stepping, run.epsilon_reset_negative) as ctx:
+        hint = 0.0
+        for _ in range(3):
+            _, hint, st = ctx.advance_host_stream(a, a, hint)
+            assert st is False
+    assert np.array_equal(a, ref[0])
