@@ -22,15 +22,18 @@ $(OBJDIR)/fv2d_stream.o: $(CSRC)/fv2d_stream.cu $(HOSTHDR)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) --fmad=false -c $< -o $@
 
-# the fused sweep: dispatcher + small kernels, and one translation unit per Riemann solver
+# the fused sweep: dispatcher + small kernels, and one translation unit per Riemann solver.
+# --fmad=false: the kernel spells its fused multiply-adds out (fma()); contraction left to the compiler
+# can differ between the copies of the unrolled row loop, which would make a row's last bit depend on
+# the work decomposition (N-GPU == 1-GPU bitwise is a contract)
 # (0 = HLL, 1 = HLLC, 2 = FSLP) holding that solver's 36 kernel instantiations (parallel under -j)
 $(OBJDIR)/fv2d_sweep.o: $(CSRC)/fv2d_sweep.cu $(HOSTHDR)
 	@mkdir -p $(OBJDIR)
-	$(NVCC) $(NVFLAGS) $(SWEEPFLAGS) -c $< -o $@
+	$(NVCC) $(NVFLAGS) --fmad=false $(SWEEPFLAGS) -c $< -o $@
 
 $(OBJDIR)/fv2d_sweep_s%.o: $(CSRC)/fv2d_sweep.cu $(HOSTHDR)
 	@mkdir -p $(OBJDIR)
-	$(NVCC) $(NVFLAGS) $(SWEEPFLAGS) -DFV2D_SOLVER_ONLY=$* -Xptxas -v -c $< -o $@ 2> $(OBJDIR)/fv2d_sweep_s$*.ptxas.log || (cat $(OBJDIR)/fv2d_sweep_s$*.ptxas.log; false)
+	$(NVCC) $(NVFLAGS) --fmad=false $(SWEEPFLAGS) -DFV2D_SOLVER_ONLY=$* -Xptxas -v -c $< -o $@ 2> $(OBJDIR)/fv2d_sweep_s$*.ptxas.log || (cat $(OBJDIR)/fv2d_sweep_s$*.ptxas.log; false)
 
 $(OBJDIR)/fv2d_capi.o: $(CSRC)/fv2d_capi.cu $(HOSTHDR)
 	@mkdir -p $(OBJDIR)

@@ -195,17 +195,23 @@ __device__ __forceinline__ FaceFlux hllc_star(const FaceState &K, double SK, dou
 template <bool FACEC>
 __device__ __forceinline__ FaceFlux hllc_f(const FaceState &L, const FaceState &R, double entho, double gamma)
 {
-  double cmax;
+  const bool lt = L.n < R.n; // one compare serves min and max
+  double SL, SR;
   if constexpr (FACEC)
-    cmax = dmax(L.c, R.c);
+  {
+    const double cmax = dmax(L.c, R.c);
+    SL                = (lt ? L.n : R.n) - cmax;
+    SR                = (lt ? R.n : L.n) + cmax;
+  }
   else
   {
+    // c = gp * x enters only as n -+ c: the product is folded into the two fmas
     const bool lfast = L.p * R.r > R.p * L.r;
-    cmax             = csound(gamma * (lfast ? L.p : R.p), lfast ? L.r : R.r);
+    const double gp  = gamma * (lfast ? L.p : R.p);
+    const double x   = csound_over_gp(gp, lfast ? L.r : R.r);
+    SL               = fma(-gp, x, lt ? L.n : R.n);
+    SR               = fma(gp, x, lt ? R.n : L.n);
   }
-  const bool lt     = L.n < R.n; // one compare serves min and max
-  const double SL   = (lt ? L.n : R.n) - cmax;
-  const double SR   = (lt ? R.n : L.n) + cmax;
 
   const double rcL = L.r * (L.n - SL);
   const double rcR = R.r * (SR - R.n);
@@ -248,11 +254,11 @@ __device__ __forceinline__ FaceFlux hllc_f(const FaceState &L, const FaceState &
   const double pK = left ? L.p : R.p;
   const double SK = left ? SL : SR;
 
-  const double EK = 0.5 * rK * (uK * uK + vK * vK) + pK * entho;
+  const double EK = fma(0.5 * rK, fma(uK, uK, vK * vK), pK * entho);
   const double d  = frcp(SK - uS);
   const double w  = SK - uK;
   const double rS = rK * w * d;
-  const double ES = (w * EK - pK * uK + pS * uS) * d;
+  const double ES = fma(pS, uS, fma(w, EK, -(pK * uK))) * d;
 
   const double r = star ? rS : rK;
   const double u = star ? uS : uK;
@@ -275,18 +281,19 @@ __device__ __forceinline__ FaceFlux hll_f(const FaceState &L, const FaceState &R
   const double SR = dmax(L.n + L.c, R.n + R.c);
 
   const double mL = L.r * L.n, mR = R.r * R.n;
-  const double EL = 0.5 * L.r * (L.n * L.n + L.t * L.t) + L.p * entho;
-  const double ER = 0.5 * R.r * (R.n * R.n + R.t * R.t) + R.p * entho;
+  const double EL = fma(0.5 * L.r, fma(L.n, L.n, L.t * L.t), L.p * entho);
+  const double ER = fma(0.5 * R.r, fma(R.n, R.n, R.t * R.t), R.p * entho);
   const double FLm = mL, FLn = fma(mL, L.n, L.p), FLt = mL * L.t, FLe = (L.p + EL) * L.n;
   const double FRm = mR, FRn = fma(mR, R.n, R.p), FRt = mR * R.t, FRe = (R.p + ER) * R.n;
 
   const double inv = frcp(SR - SL);
   const double ss  = SL * SR;
   FaceFlux f;
-  f.m    = ((SR * FLm - SL * FRm) + ss * (R.r - L.r)) * inv;
-  f.n    = ((SR * FLn - SL * FRn) + ss * (mR - mL)) * inv;
-  f.t    = ((SR * FLt - SL * FRt) + ss * (R.r * R.t - L.r * L.t)) * inv;
-  f.e    = ((SR * FLe - SL * FRe) + ss * (ER - EL)) * inv;
+  // (SR FL - SL FR + SL SR (UR - UL)) / (SR - SL), one fma per term
+  f.m    = fma(ss, R.r - L.r, fma(SR, FLm, -(SL * FRm))) * inv;
+  f.n    = fma(ss, mR - mL, fma(SR, FLn, -(SL * FRn))) * inv;
+  f.t    = fma(ss, fma(R.r, R.t, -(L.r * L.t)), fma(SR, FLt, -(SL * FRt))) * inv;
+  f.e    = fma(ss, ER - EL, fma(SR, FLe, -(SL * FRe))) * inv;
   f.pout = 0.5 * (L.p + R.p);
   if (SL >= 0.0)
   {
@@ -304,11 +311,11 @@ __device__ __forceinline__ FaceFlux fslp_f(const FaceState &L, const FaceState &
 {
   const double ai    = K * dmax(L.r * L.c, R.r * R.c);
   const double theta = dmin(1.0, dmax(fabs(L.n) * frcp(L.c), fabs(R.n) * frcp(R.c)));
-  const double ustar = 0.5 * (R.n + L.n) - 0.5 * frcp(ai) * (R.p - L.p - 0.5 * (L.r + R.r) * gdx);
-  const double Pi    = 0.5 * (R.p + L.p) - theta * 0.5 * ai * (R.n - L.n);
+  const double ustar = fma(-0.5 * frcp(ai), fma(-0.5 * (L.r + R.r), gdx, R.p - L.p), 0.5 * (R.n + L.n));
+  const double Pi    = fma(-(theta * 0.5 * ai), R.n - L.n, 0.5 * (R.p + L.p));
   const bool up      = ustar > 0.0;
   const double r = up ? L.r : R.r, n = up ? L.n : R.n, t = up ? L.t : R.t, p = up ? L.p : R.p;
-  const double E = 0.5 * r * (n * n + t * t) + p * entho;
+  const double E = fma(0.5 * r, fma(n, n, t * t), p * entho);
   FaceFlux f;
   f.m    = ustar * r;
   f.n    = fma(f.m, n, Pi);
@@ -355,12 +362,12 @@ __device__ __forceinline__ ViscFlux visc_face(double n_hi, double n_lo, double t
   const double dtdn = rdn * (t_hi - t_lo);
   const double dndt = 0.25 * rdt * (n_hi_p - n_hi_m + n_lo_p - n_lo_m);
   const double dtdt = 0.25 * rdt * (t_hi_p - t_hi_m + t_lo_p - t_lo_m);
-  const double tnn  = c43 * dndn - c23 * dtdt;
+  const double tnn  = fma(c43, dndn, -(c23 * dtdt));
   const double tnt  = dtdn + dndt;
   ViscFlux f;
   f.n = tnn;
   f.t = tnt;
-  f.e = tnn * (0.5 * (n_hi + n_lo)) + tnt * (0.5 * (t_hi + t_lo));
+  f.e = fma(tnn, 0.5 * (n_hi + n_lo), tnt * (0.5 * (t_hi + t_lo)));
   return f;
 }
 
@@ -896,7 +903,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
         if constexpr (DIFF)
         {
           // diffusive flux through the left x-face of (col, k): cells (col-1, k) and (col, k)
-          fx.e -= kaprdx * (Tk - S.X1T[par][tl]); // FL (ThermalConduction.h:64)
+          fx.e = fma(-kaprdx, Tk - S.X1T[par][tl], fx.e); // FL (ThermalConduction.h:64)
           {
             const ViscFlux vf = visc_face(S.ring[s0][1][t], S.ring[s0][1][tl], S.ring[s0][2][t], S.ring[s0][2][tl],          //
                                           S.ring[s1][1][t], S.ring[sm1][1][t], S.ring[s1][1][tl], S.ring[sm1][1][tl], //
@@ -1039,15 +1046,19 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
         }
 
         double u4[4];
-        u4[0] = un[0] + (fxl.m - fxr.m) * dtdx + (fyl[0] - fyh[0]) * dtdy;
-        u4[1] = un[1] + (fxl.n - fxr.n) * dtdx + (fyl[1] - fyh[1]) * dtdy;
-        u4[2] = un[2] + (fxl.t - fxr.t) * dtdx + (fyl[2] - fyh[2]) * dtdy;
-        u4[3] = un[3] + (fxl.e - fxr.e) * dtdx + (fyl[3] - fyh[3]) * dtdy;
+        // (every multiply-add of this kernel is spelled out as an fma and the file is compiled with
+        //  --fmad=false: left to the compiler, the copies of the unrolled row loop can contract the
+        //  same expression differently, and a row's last bit would depend on where its work item starts)
+        u4[0] = fma(fyl[0] - fyh[0], dtdy, fma(fxl.m - fxr.m, dtdx, un[0]));
+        u4[1] = fma(fyl[1] - fyh[1], dtdy, fma(fxl.n - fxr.n, dtdx, un[1]));
+        u4[2] = fma(fyl[2] - fyh[2], dtdy, fma(fxl.t - fxr.t, dtdx, un[2]));
+        u4[3] = fma(fyl[3] - fyh[3], dtdy, fma(fxl.e - fxr.e, dtdx, un[3]));
         if constexpr (GRAV != 0)
         {
           // Update.h:161-166: both sweeps add into IV (Q4)
-          u4[2] += dt * rho_k * gxv + dt * rho_k * gyv;
-          u4[3] += dt * 0.5 * (fxl.m + fxr.m) * gxv + dt * 0.5 * (fyl[0] + fyh[0]) * gyv;
+          const double dr = dt * rho_k, hdt = dt * 0.5;
+          u4[2] += fma(dr, gxv, dr * gyv);
+          u4[3] += fma(hdt * (fxl.m + fxr.m), gxv, hdt * (fyl[0] + fyh[0]) * gyv);
         }
 
         if constexpr (GRAV == 2)
@@ -1057,13 +1068,13 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
           // Applied as an in-place correction on the two rows it concerns (for the low face the
           // roll below already dropped the hyperbolic part of the carried flux).
           if (k == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL)
-            u4[2] += dtdy * (fy_hi.pout - rho_k * gyv * p.dy);
+            u4[2] = fma(dtdy, fma(-(rho_k * gyv), p.dy, fy_hi.pout), u4[2]);
           else if (k == p.jend - 1 && a.kp.edge_hi == EDGE_PHYSICAL)
           {
-            u4[0] += dtdy * fy_hi.m;
-            u4[1] += dtdy * fy_hi.t;
-            u4[2] += dtdy * (fy_hi.n - (fy_lo.pout + rho_k * gyv * p.dy));
-            u4[3] += dtdy * fy_hi.e - dt * 0.5 * fy_hi.m * gyv;
+            u4[0] = fma(dtdy, fy_hi.m, u4[0]);
+            u4[1] = fma(dtdy, fy_hi.t, u4[1]);
+            u4[2] = fma(dtdy, fy_hi.n - fma(rho_k * gyv, p.dy, fy_lo.pout), u4[2]);
+            u4[3] += fma(dtdy, fy_hi.e, -(dt * 0.5 * fy_hi.m * gyv));
           }
         }
 
@@ -1086,14 +1097,14 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
               const double FL = kap * (TC - TL) * rdx;
               const double FLb =
                   (p.bctc_ymin == FV2D_BCTC_FIXED_TEMPERATURE) ? kap * 2.0 * (TC - p.bctc_ymin_value) * rdy : kap * p.bctc_ymin_value;
-              u4[3] += dtdx * (FL - FLb);
+              u4[3] = fma(dtdx, FL - FLb, u4[3]);
             }
             if (row_hi)
             {
               const double FR = kap * (TR - TC) * rdx;
               const double FRb =
                   (p.bctc_ymax == FV2D_BCTC_FIXED_TEMPERATURE) ? kap * 2.0 * (p.bctc_ymax_value - TC) * rdy : kap * p.bctc_ymax_value;
-              u4[3] += dtdx * (FRb - FR);
+              u4[3] = fma(dtdx, FRb - FR, u4[3]);
             }
           }
         }

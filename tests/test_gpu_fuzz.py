@@ -4,7 +4,9 @@ Same generator as tests/golden/fuzz_oracle_vs_reference.py (which pins the CPU o
 bit-for-bit on the reference itself, 6000 cases, dev container): here the oracle is the checker.
   * operator-level CUDA path: bit-identical to the oracle (dt sequence, Q, U);
   * fused sweep: within the parity bar of BASELINE.json (relative L1 <= 1e-12 on the state
-    vector, dt <= 1e-13) whenever the run is regular (finite, no negative-state resets).
+    vector, dt <= 1e-13) whenever the run is regular (finite, no negative-state resets);
+  * streamed host path (fv2d_advance_host_stream, 16-row blocks): the same bar on Q, and hint /
+    no hint give the same bits.
 """
 import sys
 
@@ -21,6 +23,11 @@ from fuzz_oracle_vs_reference import draw  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 NSTEPS = 6
+
+
+@pytest.fixture(autouse=True)
+def small_stream_blocks(monkeypatch):
+    monkeypatch.setenv("FV2D_STREAM_ROWS", "16")
 
 
 def _overrides_for_capi(ov):
@@ -77,4 +84,22 @@ def test_random_configurations(seed):
         da, db = O.domain(dev, Uf), O.domain(dev, Uo)
         assert float(np.sum(np.abs(da - db))) <= 1e-12 * float(np.sum(np.abs(db))), tag
         regular += 1
+        # --- streamed host path (one step per call, state on the host, hint chain): the same bar, and
+        #     the same bits whether a call speculates on the hint or takes the serial route
+        outs = []
+        for use_hints in (True, False):
+            a, b, hint, used = Q0.copy(), np.empty_like(Q0), 0.0, []
+            with capi.Context(dev, run.time_stepping, run.epsilon_reset_negative) as ctx:
+                for _k in range(NSTEPS):
+                    du, nxt, _st = ctx.advance_host_stream(a, b, hint if use_hints else 0.0)
+                    used.append(du)
+                    hint = nxt
+                    a, b = b, a
+                negs = ctx.negative_counts()
+            outs.append((a, np.array(used), negs))
+        assert np.array_equal(outs[0][0], outs[1][0], equal_nan=True) and np.array_equal(outs[0][1], outs[1][1]), tag
+        if outs[0][2] == [0, 0, 0]:
+            assert np.max(np.abs(outs[0][1] - dts_o) / dts_o) <= 1e-13, tag
+            qa, qb = O.domain(dev, outs[0][0]), O.domain(dev, Qo)
+            assert float(np.sum(np.abs(qa - qb))) <= 1e-12 * float(np.sum(np.abs(qb))), tag
     assert checked >= 20 and regular >= 10
