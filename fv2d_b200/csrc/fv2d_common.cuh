@@ -91,6 +91,13 @@ struct KParams
   DevScalars *peer_sc[kMaxRanks]; // every rank's scalars, mapped into this device (self included)
 };
 
+// Does the slab hold the first / last row of the GLOBAL grid?  The reference ties the well-balanced
+// boundary flux (Update.h:148-156) and the conduction boundary values (ThermalConduction.h:77-103) to
+// the rows j == jbeg / j == jend - 1 whatever the boundary type - also with a periodic y boundary,
+// where the slab's edge is a neighbour slab (EDGE_NEIGHBOUR) and not a physical edge.
+__host__ __device__ inline bool holds_global_first_row(const KParams &kp) { return kp.j_global_offset == 0; }
+__host__ __device__ inline bool holds_global_last_row(const KParams &kp) { return kp.j_global_offset + kp.p.Ny == kp.Ny_global; }
+
 // Monotone map double -> uint64 so that atomicMax on the integer orders like the double.
 __host__ __device__ inline unsigned long long encode_ordered(double x)
 {

@@ -313,8 +313,8 @@ __device__ __forceinline__ void update_along_dir(const KParams &kp, const double
   // Update.h:148-156; only at the GLOBAL y boundary
   if (p.well_balanced_flux_at_y_bc && dir == FV2D_IY)
   {
-    const bool lo = (j == p.jbeg) && kp.edge_lo == EDGE_PHYSICAL;
-    const bool hi = (j == p.jend - 1) && kp.edge_hi == EDGE_PHYSICAL;
+    const bool lo = (j == p.jbeg) && holds_global_first_row(kp);
+    const bool hi = (j == p.jend - 1) && holds_global_last_row(kp);
     if (lo || hi)
     {
       const double g = get_gravity(kp, j, dir);
@@ -385,14 +385,14 @@ __global__ void k_thermal_conduction(KParams kp, const double *__restrict__ Q, d
   double FD = kappaD * (TD - TC) / dy;
 
   // ThermalConduction.h:75-103: the y-boundary overrides replace FL / FR (Q7a)
-  if (j == p.jbeg && kp.edge_lo == EDGE_PHYSICAL && p.bctc_ymin != FV2D_BCTC_NONE)
+  if (j == p.jbeg && holds_global_first_row(kp) && p.bctc_ymin != FV2D_BCTC_NONE)
   {
     if (p.bctc_ymin == FV2D_BCTC_FIXED_TEMPERATURE)
       FL = kappaL * 2.0 * (TC - p.bctc_ymin_value) / dy;
     else if (p.bctc_ymin == FV2D_BCTC_FIXED_GRADIENT)
       FL = kappaL * p.bctc_ymin_value;
   }
-  if (j == p.jend - 1 && kp.edge_hi == EDGE_PHYSICAL && p.bctc_ymax != FV2D_BCTC_NONE)
+  if (j == p.jend - 1 && holds_global_last_row(kp) && p.bctc_ymax != FV2D_BCTC_NONE)
   {
     if (p.bctc_ymax == FV2D_BCTC_FIXED_TEMPERATURE)
       FR = kappaR * 2.0 * (p.bctc_ymax_value - TC) / dy;

@@ -683,6 +683,9 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
   const long long pitchB = (long long)L.pitch * (long long)sizeof(double);
   const long long planeB = L.plane * (long long)sizeof(double);
   const bool fold   = a.fold_ghosts != 0;
+  // rows jbeg / jend-1 of the GLOBAL grid carry the well-balanced flux and the conduction boundary
+  // values, whatever the boundary type (a periodic ring of slabs has them too)
+  const bool glob_lo = holds_global_first_row(a.kp), glob_hi = holds_global_last_row(a.kp);
 
   double inv_dt_max = -1.7976931348623157e308;
 #ifdef FV2D_TIMING
@@ -1067,9 +1070,9 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
           // flux of that face by {0, 0, pout -+ rho g dy, 0}; the diffusive part of the face stays.
           // Applied as an in-place correction on the two rows it concerns (for the low face the
           // roll below already dropped the hyperbolic part of the carried flux).
-          if (k == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL)
+          if (k == p.jbeg && glob_lo)
             u4[2] = fma(dtdy, fma(-(rho_k * gyv), p.dy, fy_hi.pout), u4[2]);
-          else if (k == p.jend - 1 && a.kp.edge_hi == EDGE_PHYSICAL)
+          else if (k == p.jend - 1 && glob_hi)
           {
             u4[0] = fma(dtdy, fy_hi.m, u4[0]);
             u4[1] = fma(dtdy, fy_hi.t, u4[1]);
@@ -1084,8 +1087,8 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
           // the cell's own x-flux FL (at jbeg) / FR (at jend-1) by a y-boundary expression (Q7a) -
           // for that cell only, not for the neighbour sharing the face.  Reproduced as a correction
           // to the face-based flux on those two rows.
-          const bool row_lo = (k == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL && p.bctc_ymin != FV2D_BCTC_NONE);
-          const bool row_hi = (k == p.jend - 1 && a.kp.edge_hi == EDGE_PHYSICAL && p.bctc_ymax != FV2D_BCTC_NONE);
+          const bool row_lo = (k == p.jbeg && glob_lo && p.bctc_ymin != FV2D_BCTC_NONE);
+          const bool row_hi = (k == p.jend - 1 && glob_hi && p.bctc_ymax != FV2D_BCTC_NONE);
           if (tc_on && (row_lo || row_hi))
           {
             const double TC = S.ring[s0][3][t] * frcp(S.ring[s0][0][t]);
@@ -1241,7 +1244,7 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
       {
         // the face below row jbeg: its hyperbolic flux will be replaced by the well-balanced one, so
         // only the diffusive part is carried (w is uniform: 1 everywhere else, and 1 * x is exact)
-        const double w = (k + 1 == p.jbeg && a.kp.edge_lo == EDGE_PHYSICAL) ? 0.0 : 1.0;
+        const double w = (k + 1 == p.jbeg && glob_lo) ? 0.0 : 1.0;
         fy_lo.m = w * fy_hi.m, fy_lo.t = fma(w, fy_hi.t, -dy_t), fy_lo.n = fma(w, fy_hi.n, -dy_n);
         fy_lo.e = fma(w, fy_hi.e, -dy_e);
       }

@@ -6,7 +6,9 @@ bit-for-bit on the reference itself, 6000 cases, dev container): here the oracle
   * fused sweep: within the parity bar of BASELINE.json (relative L1 <= 1e-12 on the state
     vector, dt <= 1e-13) whenever the run is regular (finite, no negative-state resets);
   * streamed host path (fv2d_advance_host_stream, 16-row blocks): the same bar on Q, and hint /
-    no hint give the same bits.
+    no hint give the same bits;
+  * y-slabs (2 or 3 contexts sharing the GPU, ghost rows and the CFL maximum exchanged in-kernel):
+    bitwise the single-slab fused run.
 """
 import sys
 
@@ -102,4 +104,13 @@ def test_random_configurations(seed):
             assert np.max(np.abs(outs[0][1] - dts_o) / dts_o) <= 1e-13, tag
             qa, qb = O.domain(dev, outs[0][0]), O.domain(dev, Qo)
             assert float(np.sum(np.abs(qa - qb))) <= 1e-12 * float(np.sum(np.abs(qb))), tag
+        # --- y-slabs (all on this one GPU): bitwise the single-slab fused run, whatever the options
+        if dev.Ny >= 12 and regular % 2 == 0:
+            from test_gpu_multigpu import _multi
+
+            nranks = 3 if dev.Ny >= 24 else 2
+            Qn, Un, dtsn = _multi(dev, run, Q0, NSTEPS, nranks, one_device=True)
+            J, I = slice(dev.jbeg, dev.jend), slice(dev.ibeg, dev.iend)
+            assert all(np.array_equal(d, fdts) for d in dtsn), tag
+            assert np.array_equal(Un[:, J, I], Uf[:, J, I]), tag
     assert checked >= 20 and regular >= 10

@@ -71,6 +71,7 @@ CASES = [
     ("gresho_rk2_32", {"mesh.Nx": 260, "mesh.Ny": 128}),     # RK2: two exchanges per step
     ("c91_64x32", {"mesh.Nx": 256, "mesh.Ny": 128}),         # gravity + WB flux at the GLOBAL edges + TC + viscosity
     ("rt_plm_32x96", {"mesh.Nx": 64, "mesh.Ny": 192}),       # reflecting, gravity
+    ("c91_bctc_64x32", {"mesh.Nx": 256, "mesh.Ny": 128, "run.boundaries_y": "periodic"}),  # ring + WB flux + TC boundary rows
 ]
 
 
@@ -99,6 +100,9 @@ ONE_DEVICE_CASES = [
     ("gresho_rk2_32", {"mesh.Nx": 260, "mesh.Ny": 128}, 2),   # RK2: two exchanges per step, halo waits that spin
     ("c91_64x32", {"mesh.Nx": 256, "mesh.Ny": 130}, 4),       # gravity + WB flux at the GLOBAL edges + TC + viscosity, uneven
     ("rt_plm_32x96", {"mesh.Nx": 64, "mesh.Ny": 192}, 8),     # reflecting, gravity, 8 slabs
+    # a periodic RING of slabs that still carries the well-balanced flux and the conduction boundary values on the
+    # global rows jbeg / jend-1 (the reference ties them to the row, not to the boundary type; found by the fuzz test)
+    ("c91_bctc_64x32", {"mesh.Nx": 256, "mesh.Ny": 96, "run.boundaries_y": "periodic"}, 3),
 ]
 
 
