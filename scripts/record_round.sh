@@ -5,7 +5,7 @@
 #   scripts/record_round.sh [tag]
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-T=${1:-r2v8}
+T=${1:-r2v9}
 timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -4 | tee gpurun_out/${T}_pytest_gpu_1gpu.txt
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | grep -v WARNING | tail -3
 echo "== racecheck"; timeout 900 compute-sanitizer --tool racecheck python scripts/sanitize_check.py 2>&1 | grep -v WARNING | tail -9 | tee gpurun_out/${T}_sanitizer_racecheck.txt

@@ -4,7 +4,7 @@
 N=${1:-8}
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-T=${2:-r2v8}
+T=${2:-r2v9}
 if [ "$N" == "8" ]; then
   timeout 600 python -m pytest tests/test_gpu_multigpu.py -q 2>&1 | tail -3 | tee gpurun_out/${T}_pytest_multigpu_8gpu.txt
 fi

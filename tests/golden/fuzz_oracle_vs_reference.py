@@ -64,6 +64,9 @@ def draw(rng):
     if rng.random() < 0.4:
         ov["viscosity.active"] = "true"
         ov["viscosity.mu"] = round(float(rng.uniform(0.0, 0.05)), 4)
+    # (drawn last, so that the configurations of earlier seeds keep everything else)
+    if rng.random() < 0.25:
+        ov["mesh.Nghosts"] = int(rng.integers(2, 5))
     return base, ov
 
 

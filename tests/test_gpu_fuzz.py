@@ -117,10 +117,10 @@ def test_random_configurations(seed):
             qa, qb = O.domain(dev, outs[0][0]), O.domain(dev, Qo)
             assert float(np.sum(np.abs(qa - qb))) <= 1e-12 * float(np.sum(np.abs(qb))), tag
         # --- y-slabs (all on this one GPU): bitwise the single-slab fused run, whatever the options
-        if dev.Ny >= 12 and regular % 2 == 0:
+        nranks = 3 if dev.Ny // 3 >= max(8, 2 * dev.Ng) else (2 if dev.Ny // 2 >= max(6, 2 * dev.Ng) else 0)
+        if nranks and regular % 2 == 0:
             from test_gpu_multigpu import _multi
 
-            nranks = 3 if dev.Ny >= 24 else 2
             Qn, Un, dtsn = _multi(dev, run, Q0, NSTEPS, nranks, one_device=True)
             J, I = slice(dev.jbeg, dev.jend), slice(dev.ibeg, dev.iend)
             assert all(np.array_equal(d, fdts) for d in dtsn), tag
