@@ -184,6 +184,14 @@ __device__ __forceinline__ void post_cfl_mail_to(const KParams &kp, int q, doubl
   __threadfence_system();
   st_relaxed_sys_u64(&kp.peer_sc[q]->mail_gen[kp.rank], gen);
 }
+// Single slab: the mailbox is this device's own memory - device scope is enough for the hand-over
+// between two launches on one stream (the system-scope fence costs a few microseconds per step).
+__device__ __forceinline__ void post_cfl_mail_local(const KParams &kp, double hyp, unsigned long long gen)
+{
+  kp.sc->mail_inv[gen & 1][0] = hyp;
+  __threadfence();
+  *(volatile unsigned long long *)&kp.sc->mail_gen[0] = gen;
+}
 // ... to every rank's mailbox (self included), by one thread (the stand-alone computeDt).
 __device__ __forceinline__ void post_cfl_mail(const KParams &kp, double hyp, unsigned long long gen)
 {

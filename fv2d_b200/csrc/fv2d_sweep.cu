@@ -636,7 +636,15 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tg0));
     if (a.use_device_dt)
     {
-      hyp = collect_cfl_mail(a.kp, a.mail_gen);
+      // single slab: the previous launch left the maximum in this device's own mailbox (device scope)
+      bool local_mail = false;
+      if (PLAIN && a.kp.nranks == 1 && *(volatile unsigned long long *)&sc->mail_gen[0] >= a.mail_gen)
+      {
+        hyp        = *(volatile double *)&sc->mail_inv[a.mail_gen & 1][0];
+        local_mail = true;
+      }
+      else // y-slabs (or no step / computeDt before this launch: the wait then times out into the fault flag)
+        hyp = collect_cfl_mail(a.kp, a.mail_gen);
       if (p.thermal_conductivity_active)
         tc = fmax(2.0 * p.kappa / (p.dx * p.dx), 2.0 * p.kappa / (p.dy * p.dy));
       if (p.viscosity_active)
@@ -647,7 +655,8 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
       if (m < visc)
         m = visc;
       dt = p.CFL / m;
-      if (sc->fault) // a wait on a peer timed out: stop advancing (the host reports the fault)
+      // a wait on a peer timed out: stop advancing (the host reports the fault; only a cross-GPU wait can)
+      if (!local_mail && sc->fault)
         dt = __longlong_as_double(0x7ff8000000000000LL);
     }
     if (blockIdx.x == 0)
@@ -1380,7 +1389,12 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
       // The sweep's last CTA: the slab's maximum goes to every rank's mailbox (self included), one
       // lane per rank - the next step's dt is reduced on the device, no host round trip.  Then the
       // device-side clock (main.cpp:83).
-      if (t < a.kp.nranks)
+      if (PLAIN && a.kp.nranks == 1)
+      {
+        if (t == 0)
+          post_cfl_mail_local(a.kp, hyp_slab, a.mail_gen + 1);
+      }
+      else if (t < a.kp.nranks)
         post_cfl_mail_to(a.kp, t, hyp_slab, a.mail_gen + 1);
       if (t == 0)
       {
