@@ -605,6 +605,71 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
   if constexpr (!PLAIN)
     wait_halo_item(a.items[blockIdx.x]); // the CTA's first item (all threads: see wait_halo_item)
 
+  // dt = CFL / max(inverse time-steps of the current state)   (ComputeDt.h:64): the hyperbolic
+  // maximum was mailed to every rank by the last CTA of the previous final-stage sweep.  Executed by
+  // thread 0 (host dt; single slab: the device's own mailbox) or by the 32 lanes of warp 1 (y-slabs).
+  const bool warp_mail = !PLAIN && a.use_device_dt != 0;
+  auto set_dt = [&]() {
+    const int lane = t & 31;
+    double dt = a.dt_host, hyp = 0.0, tc = p.epsilon, visc = p.epsilon;
+    unsigned long long tg0 = 0, tg1 = 0;
+    if (blockIdx.x == 0 && lane == 0)
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tg0));
+    if (a.use_device_dt)
+    {
+      bool local_mail = false;
+      if constexpr (PLAIN)
+      {
+        // single slab: the previous launch left the maximum in this device's own mailbox (device scope)
+        if (a.kp.nranks == 1 && *(volatile unsigned long long *)&sc->mail_gen[0] >= a.mail_gen)
+        {
+          hyp        = *(volatile double *)&sc->mail_inv[a.mail_gen & 1][0];
+          local_mail = true;
+        }
+        else // (no step / computeDt before this launch: the wait times out into the fault flag)
+          hyp = collect_cfl_mail(a.kp, a.mail_gen);
+      }
+      else
+      {
+        double m = -1.7976931348623157e308;
+        if (lane < a.kp.nranks)
+        {
+          wait_ge_sys(&sc->mail_gen[lane], a.mail_gen, sc);
+          m = ld_relaxed_sys_f64(&sc->mail_inv[a.mail_gen & 1][lane]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+          m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        hyp = m;
+      }
+      if (p.thermal_conductivity_active)
+        tc = fmax(2.0 * p.kappa / (p.dx * p.dx), 2.0 * p.kappa / (p.dy * p.dy));
+      if (p.viscosity_active)
+        visc = fmax(2.0 * p.mu / (p.dx * p.dx), 2.0 * p.mu / (p.dy * p.dy));
+      double m = hyp;
+      if (m < tc)
+        m = tc;
+      if (m < visc)
+        m = visc;
+      dt = p.CFL / m;
+      // a wait on a peer timed out: stop advancing (the host reports the fault; only a cross-GPU wait can)
+      if (!local_mail && *(volatile unsigned int *)&sc->fault)
+        dt = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    if (lane == 0)
+    {
+      if (blockIdx.x == 0)
+      {
+        // how long this rank waited for the other ranks' CFL mails (0 on a single slab): the per-step
+        // synchronisation cost of the y-slab decomposition, reported by bench.py
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tg1));
+        sc->tstamp[0] = tg0, sc->tstamp[1] = tg1, sc->tstamp[3] += tg1 - tg0;
+      }
+      S.dt      = dt;
+      S.inv3[0] = hyp, S.inv3[1] = tc, S.inv3[2] = visc;
+    }
+  };
+
   // ---- part 2 (thread 0): the initial fill of both rings FIRST (so the rows travel while the rest is
   // set up), the second work item, and this step's dt
   if (t == 0)
@@ -628,46 +693,16 @@ k_sweep(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtenso
     const WorkItem e1 = a.items[i1]; // items[n_items] is the end marker
     S.item[1] = e1;
     publish_next(e1);
-    // dt = CFL / max(inverse time-steps of the current state)   (ComputeDt.h:64): the hyperbolic
-    // maximum was mailed to every rank by the last CTA of the previous final-stage sweep
-    double dt = a.dt_host, hyp = 0.0, tc = p.epsilon, visc = p.epsilon;
-    unsigned long long tg0 = 0, tg1 = 0;
-    if (blockIdx.x == 0)
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tg0));
-    if (a.use_device_dt)
-    {
-      // single slab: the previous launch left the maximum in this device's own mailbox (device scope)
-      bool local_mail = false;
-      if (PLAIN && a.kp.nranks == 1 && *(volatile unsigned long long *)&sc->mail_gen[0] >= a.mail_gen)
-      {
-        hyp        = *(volatile double *)&sc->mail_inv[a.mail_gen & 1][0];
-        local_mail = true;
-      }
-      else // y-slabs (or no step / computeDt before this launch: the wait then times out into the fault flag)
-        hyp = collect_cfl_mail(a.kp, a.mail_gen);
-      if (p.thermal_conductivity_active)
-        tc = fmax(2.0 * p.kappa / (p.dx * p.dx), 2.0 * p.kappa / (p.dy * p.dy));
-      if (p.viscosity_active)
-        visc = fmax(2.0 * p.mu / (p.dx * p.dx), 2.0 * p.mu / (p.dy * p.dy));
-      double m = hyp;
-      if (m < tc)
-        m = tc;
-      if (m < visc)
-        m = visc;
-      dt = p.CFL / m;
-      // a wait on a peer timed out: stop advancing (the host reports the fault; only a cross-GPU wait can)
-      if (!local_mail && sc->fault)
-        dt = __longlong_as_double(0x7ff8000000000000LL);
-    }
-    if (blockIdx.x == 0)
-    {
-      // how long this rank waited for the other ranks' CFL mails (0 on a single slab): the per-step
-      // synchronisation cost of the y-slab decomposition, reported by bench.py
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tg1));
-      sc->tstamp[0] = tg0, sc->tstamp[1] = tg1, sc->tstamp[3] += tg1 - tg0;
-    }
-    S.dt      = dt;
-    S.inv3[0] = hyp, S.inv3[1] = tc, S.inv3[2] = visc;
+    if (!warp_mail)
+      set_dt(); // host dt, or a single slab's own mailbox
+  }
+  // y-slabs: warp 1 collects the ranks' CFL mails - one lane per rank, so the mailboxes are polled side
+  // by side (a single thread walking them pays one system-scope round trip per rank) - while thread 0
+  // sets up the rings and the work queue
+  if constexpr (!PLAIN)
+  {
+    if (warp_mail && t >= 32 && t < 64)
+      set_dt();
   }
   __syncthreads();
 
