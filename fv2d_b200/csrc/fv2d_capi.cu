@@ -110,19 +110,6 @@ static int make_tmap(CUtensorMap *out, double *base, const Layout &L, int box_co
 
 static size_t array_bytes(const Layout &L) { return (size_t)4 * L.plane * sizeof(double); }
 
-static int ensure_stage(fv2d_ctx *c, size_t bytes)
-{
-  if (c->stage_bytes >= bytes)
-    return FV2D_OK;
-  if (c->stage_host)
-    cudaFreeHost(c->stage_host);
-  c->stage_host  = nullptr;
-  c->stage_bytes = 0;
-  FV2D_CUDA(cudaMallocHost(&c->stage_host, bytes));
-  c->stage_bytes = bytes;
-  return FV2D_OK;
-}
-
 // host [f][rows][Ntx] <-> device padded planes
 static int copy_h2d(fv2d_ctx *c, double *dev, const double *host)
 {
