@@ -280,3 +280,70 @@ def test_io_errors_are_reported_not_thrown(tmp_path):
     with pytest.raises(capi.Fv2dError) as e:
         capi.io_save_solution(dev, run, capi.init_problem(dev, run), 0, 0.0)
     assert e.value.code == 3  # FV2D_ERR_IO
+
+
+# ---------------------------------------------------------------------------- the writer against libhdf5's own bytes
+
+
+def _messages(path):
+    """(object path, message type, flags, body) of every object-header message of a file."""
+    f = h5mini.File(path)
+    out = []
+
+    def rec(node, name):
+        for mtype, mflags, body in node.messages:
+            out.append((name, mtype, mflags, bytes(body)))
+        if node.is_group:
+            for k in node.keys():
+                rec(node[k], name + "/" + k)
+
+    rec(f, "")
+    return f, out
+
+
+@pytest.mark.skipif(SCIPY_FIXTURE is None, reason="scipy's MATLAB HDF5 fixture not installed")
+def test_writer_uses_the_encodings_the_real_hdf5_library_wrote(tmp_path):
+    """No libhdf5 can open our files here (f-2 stays unpinned), but the pieces can be held against
+    bytes that libhdf5 itself produced: the one file in this image written by the real library (the
+    MATLAB fixture the reader is pinned on) contains a double dataset with an attribute, i.e. the same
+    message kinds run.h5 is made of.  The IEEE double datatype message must be byte for byte libhdf5's,
+    dataspace / attribute / symbol-table messages must use the same versions and padding rules, the
+    superblock the same version, offset sizes and B-tree parameters."""
+    dev, run = _params(tmp_path)
+    capi.io_save_solution(dev, run, _state(dev, run), 0, 0.0)
+    ours_f, ours = _messages(tmp_path / "run.h5")
+    ref_f, ref = _messages(SCIPY_FIXTURE)
+
+    assert (ours_f.sb_version, ours_f.leaf_k, ours_f.internal_k) == (ref_f.sb_version, ref_f.leaf_k, ref_f.internal_k)
+    assert ours_f.free_addr == ref_f.free_addr == h5mini.UNDEF and ours_f.driver == ref_f.driver == h5mini.UNDEF
+
+    def of_type(msgs, t):
+        return [m for m in msgs if m[1] == t]
+
+    # datatype of every float dataset: libhdf5's H5T_IEEE_F64LE encoding, all 24 bytes
+    ref_double = [m[3] for m in of_type(ref, 0x0003) if m[3][0] & 0x0F == 1]
+    assert len(ref_double) == 1
+    ours_double = [m[3] for m in of_type(ours, 0x0003)]
+    assert len(ours_double) == 6 and all(b == ref_double[0] for b in ours_double)  # x, y, rho, u, v, prs
+    # dataspace: version 1, no permutation / max-dims flags beyond what libhdf5 set, 8 bytes per dimension
+    for _, _, _, b in of_type(ours, 0x0001):
+        rb = of_type(ref, 0x0001)[0][3]
+        assert b[0] == rb[0] == 1 and b[2] == rb[2] and len(b) == 8 + 8 * b[1]
+    # attributes: version 1 with name / datatype / dataspace each padded to 8 bytes, like libhdf5's
+    ref_attr = of_type(ref, 0x000C)[0][3]
+    assert ref_attr[0] == 1
+    for _, _, _, b in of_type(ours, 0x000C):
+        assert b[0] == 1 and b[1] == 0
+        nsz, tsz, ssz = struct.unpack_from("<HHH", b, 2)
+        data = len(b) - 8 - sum((n + 7) // 8 * 8 for n in (nsz, tsz, ssz))
+        assert data >= 0 and b[8 + nsz - 1] == 0  # NUL-terminated name counted in its size, as in the fixture
+    rn = struct.unpack_from("<H", ref_attr, 2)[0]
+    assert ref_attr[8 + rn - 1] == 0
+    # groups: old-style symbol-table message (B-tree + local heap address), 16 bytes, as the fixture's root
+    assert all(len(m[3]) == 16 for m in of_type(ours, 0x0011)) and len(of_type(ref, 0x0011)[0][3]) == 16
+    # contiguous layout (version 3 = the HDF5 1.8 default; the 2004 fixture still has version 2) and fill
+    # value message versions libhdf5 1.8 reads (1, 2)
+    assert all(m[3][0] == 3 and m[3][1] == 1 for m in of_type(ours, 0x0008))
+    assert all(m[3][0] in (1, 2) for m in of_type(ours, 0x0005))
+    # every message body is a multiple of 8 bytes (object header version 1 alignment rule)
+    assert all(len(m[3]) % 8 == 0 for m in ours) and all(len(m[3]) % 8 == 0 for m in ref)
