@@ -72,3 +72,17 @@ def test_handle_allgather_world_size_2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True, 2.0), (1, True, 2.0)]
+
+
+def test_numa_binding_is_best_effort():
+    """bench.py binds every rank to its GPU's NUMA node before it allocates host arrays; on a box without
+    a GPU (or without NUMA information) the helper must report, not raise, and leave the affinity alone."""
+    import os
+
+    from fv2d_b200 import multigpu
+
+    before = os.sched_getaffinity(0)
+    info = multigpu.bind_to_gpu_numa_node(0)
+    assert info["device"] == 0 and ("error" in info or info["numa_node"] is not None)
+    if info.get("cpus") is None:
+        assert os.sched_getaffinity(0) == before
